@@ -1,0 +1,204 @@
+/*
+ * octree_cuc.h -- C ABI of the B200 octree render connector ("cuc" = CUDA connector).
+ *
+ * Drop-in replacement for the reference's GL connector
+ *   /root/reference/src/qubatron/octree_glc.c   (header part L1-87)
+ * The three reference entry points keep their names, argument order, argument
+ * meaning and (absent) error convention, so qubatron.c / modelutil.c compile
+ * against this header unchanged:
+ *
+ *   octree_glc_init                   replaces octree_glc.c L65,  L93-247
+ *   octree_glc_update                 replaces octree_glc.c L66-76, L249-352
+ *   octree_glc_upload_texbuffer_data  replaces octree_glc.c L77-85, L361-498
+ *   octree_glc_buffer_t               replaces octree_glc.c L16-24
+ *   octree_glc_t                      replaces octree_glc.c L26-63 (only `memsize`
+ *                                     is read outside the connector, qubatron.c L558)
+ *
+ * Everything named octree_cuc_* is an extension the headless / multi-GPU use
+ * needs and the GL connector never had (the reference has no readback at all).
+ *
+ * Plain C, no CUDA or torch types: device buffers cross the boundary as
+ * void* / uint64_t addresses.
+ */
+#ifndef OCTREE_CUC_H
+#define OCTREE_CUC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* mt_math/mt_vector_3d.c L6-10: passed BY VALUE to octree_glc_update */
+#ifndef mt_vector_3d_h
+typedef struct _v3_t v3_t;
+struct _v3_t
+{
+    float x, y, z;
+};
+#endif
+
+/* values of the GL enums the reference passes as `type` (modelutil.c L227-255) */
+#define OCTREE_CUC_GL_INT 0x1404
+#define OCTREE_CUC_GL_FLOAT 0x1406
+
+/* octree_glc.c L16-24 */
+typedef enum _octree_glc_buffer_t
+{
+    OCTREE_GLC_BUFFER_STATIC_COLOR,
+    OCTREE_GLC_BUFFER_STATIC_NORMAL,
+    OCTREE_GLC_BUFFER_STATIC_OCTREE,
+    OCTREE_GLC_BUFFER_DYNAMIC_COLOR,
+    OCTREE_GLC_BUFFER_DYNAMIC_NORMAL,
+    OCTREE_GLC_BUFFER_DYNAMIC_OCTREE
+} octree_glc_buffer_t;
+
+/* octree_glc.c L26-63.  A value struct, returned by value from init and passed
+ * by pointer afterwards.  `memsize` keeps the reference's name and meaning
+ * (bytes of device storage, saturating at UINT32_MAX like the GLuint it was);
+ * `memsize_bytes` is the unsaturated figure. */
+typedef struct octree_glc_t
+{
+    void*        impl; /* connector state, owned by the connector */
+    uint64_t     memsize_bytes;
+    unsigned int memsize;
+} octree_glc_t;
+
+/* ---- reference API ------------------------------------------------------ */
+
+/* octree_glc.c L93: `path` was the shader directory; accepted and ignored
+ * (kernels are compiled into the library).  Uses the current CUDA device
+ * (device 0 unless octree_cuc_select_device was called first).  Aborts with a
+ * message when no CUDA device is usable -- there is no CPU fallback. */
+octree_glc_t octree_glc_init(char* path);
+
+/* octree_glc.c L249: render one frame.  Flushes pending range uploads, sets the
+ * uniforms exactly as L263-284 (render size = width/(6 - quality/2), light from
+ * lightc and lighta, base cube (0,S,S,S)), clears to (0,0,0,0) and runs the
+ * trace+shadow+shade kernel.  Asynchronous like a GL draw: the frame is complete
+ * after octree_cuc_sync / octree_cuc_read_frame.  The blit to a window and the
+ * crosshair (L310-351) are presentation and are not done. */
+void octree_glc_update(octree_glc_t* rc, float width, float height, v3_t position, v3_t angle, float lighta,
+                       uint8_t quality, int maxlevel, float basesize, int shoot);
+
+/* octree_glc.c L361: `data` points at the START of the whole logical array;
+ * bytes [floor(start/itemsize)*itemsize, floor(end/itemsize)*itemsize) are
+ * copied to the same offsets of the device array.  `size` only drives
+ * capacity; when the array has to grow the call uploads [0,size) like the
+ * reference does (L412-428).  type/itemsize: GL_FLOAT/12 for colour and
+ * normal arrays, GL_INT/16 for octree arrays (a node = 3 items = 12 ints).
+ * `data` has been consumed when the call returns. */
+void octree_glc_upload_texbuffer_data(octree_glc_t* rc, void* data, int type, size_t size, size_t itemsize,
+                                      size_t start, size_t end, octree_glc_buffer_t buftype);
+
+/* ---- extensions ---------------------------------------------------------- */
+
+/* choose the CUDA device used by the next octree_glc_init (default: current) */
+void octree_cuc_select_device(int device);
+
+/* release all device memory of the connector */
+void octree_cuc_destroy(octree_glc_t* rc);
+
+/* wait for all queued uploads and frames */
+void octree_cuc_sync(octree_glc_t* rc);
+
+/* size of the last rendered frame */
+void octree_cuc_frame_size(octree_glc_t* rc, int* width, int* height);
+
+/* copy the last frame (RGBA8, row 0 = bottom like glReadPixels) to host memory;
+ * synchronises.  Returns bytes written. */
+size_t octree_cuc_read_frame(octree_glc_t* rc, uint8_t* rgba_host, size_t capacity);
+
+/* device address of the RGBA8 frame (valid until the next resize) */
+uint64_t octree_cuc_frame_device(octree_glc_t* rc);
+
+/* render straight into caller-owned device memory (e.g. a torch tensor or a
+ * peer-mapped buffer of another GPU); 0 restores the internal framebuffer.
+ * pitch_pixels = row stride in pixels (0 = frame width). */
+void octree_cuc_set_frame_target(octree_glc_t* rc, uint64_t device_ptr, size_t pitch_pixels);
+
+/* parity planes: when enabled every frame also writes flags (1 byte/pixel,
+ * OCTREE_CUC_FLAG_*) and aux (6 int32/pixel, OCTREE_CUC_AUX_*) */
+void   octree_cuc_enable_aux(octree_glc_t* rc, int enable);
+size_t octree_cuc_read_aux(octree_glc_t* rc, uint8_t* flags_host, int32_t* aux_host);
+
+enum
+{
+    OCTREE_CUC_FLAG_DISCARD   = 1,
+    OCTREE_CUC_FLAG_LEAF      = 2,
+    OCTREE_CUC_FLAG_SHADED    = 4,
+    OCTREE_CUC_FLAG_LIT       = 8,
+    OCTREE_CUC_FLAG_DISC_TEST = 16,
+    OCTREE_CUC_FLAG_DISC_ON   = 32
+};
+enum
+{
+    OCTREE_CUC_AUX_MODEL_S   = 0,
+    OCTREE_CUC_AUX_MODEL_D   = 1,
+    OCTREE_CUC_AUX_NODE_S    = 2,
+    OCTREE_CUC_AUX_NODE_D    = 3,
+    OCTREE_CUC_AUX_SH_NODE_S = 4,
+    OCTREE_CUC_AUX_SH_NODE_D = 5,
+    OCTREE_CUC_AUX_STRIDE    = 6
+};
+
+/* work counters of the last frame (SURVEY.md 8d counting rule); counting is a
+ * separate kernel instantiation, enabled per frame */
+typedef struct octree_cuc_counters
+{
+    int64_t rays_primary;
+    int64_t rays_shadow;
+    int64_t rays_disc;
+    int64_t expand_s;
+    int64_t expand_d;
+    int64_t leaf_s;
+    int64_t leaf_d;
+    int64_t hits;
+    int64_t discards;
+    int64_t descents;
+} octree_cuc_counters;
+void octree_cuc_enable_counters(octree_glc_t* rc, int enable);
+void octree_cuc_read_counters(octree_glc_t* rc, octree_cuc_counters* out);
+
+/* image-tile sharding (multi-GPU): this connector renders only tiles whose
+ * index (row-major over tile_w x tile_h tiles) is congruent to `rank` modulo
+ * `world`.  world = 1 renders everything (default).  Pixels of other ranks'
+ * tiles are left untouched. */
+void octree_cuc_set_shard(octree_glc_t* rc, int rank, int world, int tile_w, int tile_h);
+
+/* light override: when set, octree_glc_update uses it instead of lightc/lighta */
+void octree_cuc_set_light(octree_glc_t* rc, const float* light_xyz_or_null);
+
+/* kernel selection: 0 = auto (fast kernel when the base cube is exactly
+ * representable at every level, generic otherwise), 1 = generic, 2 = fast */
+void octree_cuc_set_kernel(octree_glc_t* rc, int which);
+int  octree_cuc_last_kernel(octree_glc_t* rc);
+
+/* device time of the last frame's kernels in milliseconds (CUDA events on the
+ * connector's stream); synchronises on the frame */
+float octree_cuc_last_frame_ms(octree_glc_t* rc);
+
+/* number of kernels this connector has launched since init */
+uint64_t octree_cuc_launch_count(octree_glc_t* rc);
+
+/* a batch of views of the same scene (multi-view config): n frames of equal
+ * size rendered back to back into one device buffer of n*W*H pixels.
+ * positions/angles: 3 floats per view. */
+void octree_cuc_update_views(octree_glc_t* rc, int n, float width, float height, const float* positions,
+                             const float* angles, float lighta, uint8_t quality, int maxlevel, float basesize,
+                             int shoot);
+
+/* multi-GPU range updates: pending ranges can be exported as one packed blob
+ * (header + payload) by the rank that received the host uploads, broadcast by
+ * the caller (NCCL), and applied on every other rank. */
+size_t octree_cuc_export_pending(octree_glc_t* rc, void* blob_host, size_t capacity);
+void   octree_cuc_apply_blob(octree_glc_t* rc, const void* blob_host, size_t bytes);
+
+/* library self-description */
+const char* octree_cuc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,232 @@
+"""ctypes bindings of the CPU oracle (oracle/octree_fsh_oracle.c) and of the
+reference's own compiled code (oracle/_ref/libqubatron_ref.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs.  Never by qubatron_b200/.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(HERE, "liboctree_fsh_oracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libqubatron_ref.so")
+REF_QMC = os.path.join(HERE, "_ref", "qmc")
+REF_GLSL = os.path.join(HERE, "_ref", "glsl_ref")
+
+AUX_STRIDE = 6
+FLAG_DISCARD, FLAG_LEAF, FLAG_SHADED, FLAG_LIT, FLAG_DISC_TEST, FLAG_DISC_ON = 1, 2, 4, 8, 16, 32
+
+
+def build(ref=True):
+    """make the oracle; `ref` also (re)builds oracle/_ref when /root/reference exists."""
+    r = subprocess.run(["make", "-C", HERE, "all"] + (["ref"] if ref else []), stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("oracle build failed:\n" + r.stdout)
+    return r.stdout
+
+
+class _Scene(C.Structure):
+    _fields_ = [("oct_s", C.c_void_p), ("nodes_s", C.c_int64), ("oct_d", C.c_void_p), ("nodes_d", C.c_int64),
+                ("col_s", C.c_void_p), ("nrm_s", C.c_void_p), ("points_s", C.c_int64),
+                ("col_d", C.c_void_p), ("nrm_d", C.c_void_p), ("points_d", C.c_int64)]
+
+
+class Uniforms(C.Structure):
+    _fields_ = [("camfp", C.c_float * 3), ("angle_in", C.c_float * 3), ("light", C.c_float * 3),
+                ("basecube", C.c_float * 4), ("dimensions", C.c_float * 2), ("maxlevel", C.c_int32),
+                ("shoot", C.c_int32), ("vp_w", C.c_int32), ("vp_h", C.c_int32)]
+
+
+class Counters(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in ("rays_primary", "rays_shadow", "rays_disc", "expand_s", "expand_d",
+                                         "leaf_s", "leaf_d", "hits", "discards", "descents")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+def algorithmic_bytes(c, pixels):
+    """32(E_s+E_d) + 4(L_s+L_d) + 24 H + 4 W H."""
+    return 32 * (c["expand_s"] + c["expand_d"]) + 4 * (c["leaf_s"] + c["leaf_d"]) + 24 * c["hits"] + 4 * pixels
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(ORACLE_SO):
+            build(ref=False)
+        l = C.CDLL(ORACLE_SO)
+        l.qb_oracle_uniforms.argtypes = [C.POINTER(Uniforms), C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_float,
+                                         C.c_uint8, C.c_int, C.c_float, C.c_int]
+        l.qb_oracle_render.argtypes = [C.POINTER(_Scene), C.POINTER(Uniforms), C.c_int, C.c_int, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.POINTER(Counters), C.c_int]
+        l.qb_oracle_trace_batch.argtypes = [C.POINTER(_Scene), C.POINTER(Uniforms), C.c_int64, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        l.qb_oracle_pixel_ray.argtypes = [C.POINTER(Uniforms), C.c_int, C.c_int, C.c_void_p]
+        _lib = l
+    return _lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
+
+
+class OracleScene:
+    """Keeps contiguous copies of a qubatron_b200.scene.Scene-like object alive for the C side."""
+
+    def __init__(self, scene):
+        self.oct_s = np.ascontiguousarray(scene.oct_s, dtype=np.int32).reshape(-1, 12)
+        self.oct_d = np.ascontiguousarray(scene.oct_d, dtype=np.int32).reshape(-1, 12)
+        self.col_s = np.ascontiguousarray(scene.col_s, dtype=np.float32).reshape(-1, 3)
+        self.nrm_s = np.ascontiguousarray(scene.nrm_s, dtype=np.float32).reshape(-1, 3)
+        self.col_d = np.ascontiguousarray(scene.col_d, dtype=np.float32).reshape(-1, 3)
+        self.nrm_d = np.ascontiguousarray(scene.nrm_d, dtype=np.float32).reshape(-1, 3)
+        self.c = _Scene(_ptr(self.oct_s), len(self.oct_s), _ptr(self.oct_d), len(self.oct_d),
+                        _ptr(self.col_s), _ptr(self.nrm_s), len(self.col_s),
+                        _ptr(self.col_d), _ptr(self.nrm_d), len(self.col_d))
+
+
+def uniforms(width, height, position, angle, lighta=0.0, quality=10, maxlevel=12, basesize=1800.0, shoot=0,
+             light=None):
+    """octree_glc_update's uniform set-up (octree_glc.c L263-284)."""
+    u = Uniforms()
+    pos = (C.c_float * 3)(*[float(v) for v in position])
+    ang = (C.c_float * 3)(*[float(v) for v in angle])
+    lib().qb_oracle_uniforms(C.byref(u), float(width), float(height), C.cast(pos, C.c_void_p),
+                             C.cast(ang, C.c_void_p), float(lighta), int(quality), int(maxlevel), float(basesize),
+                             int(shoot))
+    if light is not None:
+        for i in range(3):
+            u.light[i] = float(light[i])
+    return u
+
+
+def render(oscene, u, rows=None, threads=0, want_aux=True):
+    """Returns dict(rgba [H,W,4] u8, flags [H,W] u8, aux [H,W,6] i32, counters dict)."""
+    W, H = u.vp_w, u.vp_h
+    rgba = np.zeros((H, W, 4), dtype=np.uint8)
+    flags = np.zeros((H, W), dtype=np.uint8) if want_aux else None
+    aux = np.full((H, W, AUX_STRIDE), -1, dtype=np.int32) if want_aux else None
+    cnt = Counters()
+    r0, r1 = (0, H) if rows is None else rows
+    lib().qb_oracle_render(C.byref(oscene.c), C.byref(u), int(r0), int(r1), _ptr(rgba), _ptr(flags), _ptr(aux),
+                           C.byref(cnt), int(threads))
+    return {"rgba": rgba, "flags": flags, "aux": aux, "counters": cnt.as_dict()}
+
+
+def trace_batch(oscene, u, pos, direction, threads=0):
+    pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 3)
+    direction = np.ascontiguousarray(direction, dtype=np.float32).reshape(-1, 3)
+    n = len(pos)
+    result = np.zeros(n, dtype=np.int32)
+    nodes = np.zeros((n, 2), dtype=np.int32)
+    models = np.zeros((n, 2), dtype=np.int32)
+    isp = np.zeros((n, 4), dtype=np.float32)
+    lib().qb_oracle_trace_batch(C.byref(oscene.c), C.byref(u), n, _ptr(pos), _ptr(direction), _ptr(result),
+                                _ptr(nodes), _ptr(models), _ptr(isp), int(threads))
+    return result, nodes, models, isp
+
+
+def pixel_rays(u):
+    """Primary ray direction of every pixel: float32 [H,W,3]."""
+    W, H = u.vp_w, u.vp_h
+    out = np.zeros((H, W, 3), dtype=np.float32)
+    d = (C.c_float * 3)()
+    l = lib()
+    for y in range(H):
+        for x in range(W):
+            l.qb_oracle_pixel_ray(C.byref(u), x, y, C.cast(d, C.c_void_p))
+            out[y, x] = (d[0], d[1], d[2])
+    return out
+
+
+# ---------------------------------------------------------------------------
+# the reference's own compiled code (octree.c unmodified), when oracle/_ref exists
+# ---------------------------------------------------------------------------
+
+def have_ref():
+    return os.path.exists(REF_SO)
+
+
+_ref = None
+
+
+def ref_lib():
+    global _ref
+    if _ref is None:
+        l = C.CDLL(REF_SO)
+        l.qbref_tree_create.restype = C.c_void_p
+        l.qbref_tree_create.argtypes = [C.c_float, C.c_int]
+        l.qbref_tree_delete.argtypes = [C.c_void_p]
+        l.qbref_tree_reset.argtypes = [C.c_void_p]
+        l.qbref_tree_insert_points.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]
+        l.qbref_tree_insert_point.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        l.qbref_tree_insert_paths.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]
+        l.qbref_tree_remove_point.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        l.qbref_tree_len.restype = C.c_int64
+        l.qbref_tree_len.argtypes = [C.c_void_p]
+        l.qbref_tree_data.restype = C.POINTER(C.c_int32)
+        l.qbref_tree_data.argtypes = [C.c_void_p]
+        l.qbref_trace_batch.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        _ref = l
+    return _ref
+
+
+class RefOctree:
+    """The reference's octree_t driven through oracle/ref_wrap.c."""
+
+    def __init__(self, basesize=1800.0, levels=12):
+        self.l = ref_lib()
+        self.h = self.l.qbref_tree_create(float(basesize), int(levels))
+
+    def insert_points(self, pts, first=0):
+        pts = np.ascontiguousarray(pts, dtype=np.float32).reshape(-1, 3)
+        self.l.qbref_tree_insert_points(self.h, _ptr(pts), len(pts), int(first))
+
+    def insert_point(self, pnt, modind):
+        p = np.ascontiguousarray(pnt, dtype=np.float32)
+        t = np.zeros(13, dtype=np.int32)
+        self.l.qbref_tree_insert_point(self.h, _ptr(p), int(modind), _ptr(t))
+        return t
+
+    def insert_paths(self, paths, first=0):
+        paths = np.ascontiguousarray(paths, dtype=np.int32).reshape(-1, 12)
+        self.l.qbref_tree_insert_paths(self.h, _ptr(paths), len(paths), int(first))
+
+    def remove_point(self, pnt):
+        p = np.ascontiguousarray(pnt, dtype=np.float32)
+        m, o = C.c_int32(-1), C.c_int32(-1)
+        self.l.qbref_tree_remove_point(self.h, _ptr(p), C.byref(m), C.byref(o))
+        return m.value, o.value
+
+    def reset(self):
+        self.l.qbref_tree_reset(self.h)
+
+    def __len__(self):
+        return int(self.l.qbref_tree_len(self.h))
+
+    def nodes(self):
+        return np.ctypeslib.as_array(self.l.qbref_tree_data(self.h), shape=(len(self), 12)).copy()
+
+    def trace(self, pos, direction, threads=0):
+        """octree_trace_line over rays: returns (oct[8] of leaf or 0, tlf [n,4])."""
+        pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 3)
+        direction = np.ascontiguousarray(direction, dtype=np.float32).reshape(-1, 3)
+        n = len(pos)
+        idx = np.zeros(n, dtype=np.int32)
+        tlf = np.zeros((n, 4), dtype=np.float32)
+        self.l.qbref_trace_batch(self.h, n, _ptr(pos), _ptr(direction), _ptr(idx), _ptr(tlf), int(threads))
+        return idx, tlf
+
+    def __del__(self):
+        try:
+            self.l.qbref_tree_delete(self.h)
+        except Exception:
+            pass

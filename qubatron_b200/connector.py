@@ -1,0 +1,255 @@
+"""ctypes mirror of the reference connector interface.
+
+The C ABI is include/octree_cuc.h; this module binds it one-to-one so that
+Python tests read like calls of the reference's octree_glc.c:
+
+    rc = OctreeGlc("shaders/")                       # octree_glc_init   (octree_glc.c L93)
+    rc.upload_texbuffer_data(arr, GL_INT, size, 16, start, end, STATIC_OCTREE)   # L361
+    rc.update(width, height, pos, angle, lighta, quality, maxlevel, basesize, shoot)  # L249
+
+There is NO fallback: if liboctree_cuc.so is missing the import of this module
+raises, and octree_glc_init aborts the process when CUDA is unusable.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from .build import lib_paths
+
+GL_INT = 0x1404
+GL_FLOAT = 0x1406
+
+# octree_glc_buffer_t (octree_glc.c L16-24)
+STATIC_COLOR, STATIC_NORMAL, STATIC_OCTREE, DYNAMIC_COLOR, DYNAMIC_NORMAL, DYNAMIC_OCTREE = range(6)
+
+FLAG_DISCARD, FLAG_LEAF, FLAG_SHADED, FLAG_LIT, FLAG_DISC_TEST, FLAG_DISC_ON = 1, 2, 4, 8, 16, 32
+AUX_MODEL_S, AUX_MODEL_D, AUX_NODE_S, AUX_NODE_D, AUX_SH_NODE_S, AUX_SH_NODE_D = range(6)
+AUX_STRIDE = 6
+
+KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FAST = 0, 1, 2
+
+
+class v3_t(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("z", C.c_float)]
+
+
+class octree_glc_t(C.Structure):
+    _fields_ = [("impl", C.c_void_p), ("memsize_bytes", C.c_uint64), ("memsize", C.c_uint)]
+
+
+class Counters(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in ("rays_primary", "rays_shadow", "rays_disc", "expand_s", "expand_d",
+                                         "leaf_s", "leaf_d", "hits", "discards", "descents")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+# every symbol include/octree_cuc.h declares (tests check the export list against the header)
+_PROTOS = {
+    "octree_glc_init": (octree_glc_t, [C.c_char_p]),
+    "octree_glc_update": (None, [C.POINTER(octree_glc_t), C.c_float, C.c_float, v3_t, v3_t, C.c_float, C.c_uint8,
+                                 C.c_int, C.c_float, C.c_int]),
+    "octree_glc_upload_texbuffer_data": (None, [C.POINTER(octree_glc_t), C.c_void_p, C.c_int, C.c_size_t,
+                                                C.c_size_t, C.c_size_t, C.c_size_t, C.c_int]),
+    "octree_cuc_select_device": (None, [C.c_int]),
+    "octree_cuc_destroy": (None, [C.POINTER(octree_glc_t)]),
+    "octree_cuc_sync": (None, [C.POINTER(octree_glc_t)]),
+    "octree_cuc_frame_size": (None, [C.POINTER(octree_glc_t), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "octree_cuc_read_frame": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_void_p, C.c_size_t]),
+    "octree_cuc_frame_device": (C.c_uint64, [C.POINTER(octree_glc_t)]),
+    "octree_cuc_set_frame_target": (None, [C.POINTER(octree_glc_t), C.c_uint64, C.c_size_t]),
+    "octree_cuc_enable_aux": (None, [C.POINTER(octree_glc_t), C.c_int]),
+    "octree_cuc_read_aux": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_void_p, C.c_void_p]),
+    "octree_cuc_enable_counters": (None, [C.POINTER(octree_glc_t), C.c_int]),
+    "octree_cuc_read_counters": (None, [C.POINTER(octree_glc_t), C.POINTER(Counters)]),
+    "octree_cuc_set_shard": (None, [C.POINTER(octree_glc_t), C.c_int, C.c_int, C.c_int, C.c_int]),
+    "octree_cuc_set_light": (None, [C.POINTER(octree_glc_t), C.c_void_p]),
+    "octree_cuc_set_kernel": (None, [C.POINTER(octree_glc_t), C.c_int]),
+    "octree_cuc_last_kernel": (C.c_int, [C.POINTER(octree_glc_t)]),
+    "octree_cuc_last_frame_ms": (C.c_float, [C.POINTER(octree_glc_t)]),
+    "octree_cuc_launch_count": (C.c_uint64, [C.POINTER(octree_glc_t)]),
+    "octree_cuc_update_views": (None, [C.POINTER(octree_glc_t), C.c_int, C.c_float, C.c_float, C.c_void_p,
+                                       C.c_void_p, C.c_float, C.c_uint8, C.c_int, C.c_float, C.c_int]),
+    "octree_cuc_export_pending": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_void_p, C.c_size_t]),
+    "octree_cuc_apply_blob": (None, [C.POINTER(octree_glc_t), C.c_void_p, C.c_size_t]),
+    "octree_cuc_version": (C.c_char_p, []),
+}
+
+_lib = None
+
+
+def load_library():
+    """dlopen liboctree_cuc.so and bind every prototype; raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_paths()["cuc"]
+    if not os.path.exists(path):
+        raise ImportError("liboctree_cuc.so is not built (run __graft_entry__.build()); "
+                          "qubatron_b200 has no CPU rendering path")
+    lib = C.CDLL(path)
+    for name, (res, args) in _PROTOS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _f3(v):
+    return v3_t(float(v[0]), float(v[1]), float(v[2]))
+
+
+class OctreeGlc:
+    """Host-side mirror of the reference connector (octree_glc.c), one instance per GPU."""
+
+    def __init__(self, path=b"", device=None):
+        self.lib = load_library()
+        if device is not None:
+            self.lib.octree_cuc_select_device(int(device))
+        if isinstance(path, str):
+            path = path.encode()
+        self.rc = self.lib.octree_glc_init(path)
+        self._p = C.byref(self.rc)
+        self._keep = None
+
+    # ---- reference API -------------------------------------------------------
+    def upload_texbuffer_data(self, data, type_, size, itemsize, start, end, buftype):
+        """octree_glc_upload_texbuffer_data: `data` = the WHOLE logical host array."""
+        arr = np.ascontiguousarray(data)
+        self.lib.octree_glc_upload_texbuffer_data(self._p, arr.ctypes.data_as(C.c_void_p), int(type_), int(size),
+                                                  int(itemsize), int(start), int(end), int(buftype))
+
+    def update(self, width, height, position, angle, lighta=0.0, quality=10, maxlevel=12, basesize=1800.0, shoot=0):
+        """octree_glc_update: render one frame (asynchronous, like a GL draw)."""
+        self.lib.octree_glc_update(self._p, float(width), float(height), _f3(position), _f3(angle), float(lighta),
+                                   int(quality), int(maxlevel), float(basesize), int(shoot))
+
+    @property
+    def memsize(self):
+        return int(self.rc.memsize_bytes)
+
+    # ---- conveniences over the reference API ----------------------------------
+    def upload_octree(self, nodes, dynamic=False, start_node=0, end_node=None):
+        """nodes: int32 [n,12] (whole array); uploads nodes [start_node,end_node)."""
+        nodes = np.ascontiguousarray(nodes, dtype=np.int32).reshape(-1, 12)
+        n = nodes.shape[0]
+        end_node = n if end_node is None else end_node
+        self.upload_texbuffer_data(nodes, GL_INT, n * 48, 16, start_node * 48, end_node * 48,
+                                   DYNAMIC_OCTREE if dynamic else STATIC_OCTREE)
+
+    def upload_points(self, arr, buftype, start_point=0, end_point=None):
+        arr = np.ascontiguousarray(arr, dtype=np.float32).reshape(-1, 3)
+        n = arr.shape[0]
+        end_point = n if end_point is None else end_point
+        self.upload_texbuffer_data(arr, GL_FLOAT, n * 12, 12, start_point * 12, end_point * 12, buftype)
+
+    def upload_scene(self, scene):
+        """The six uploads of modelutil_load_flat (modelutil.c L227-321)."""
+        self.upload_points(scene.col_s, STATIC_COLOR)
+        self.upload_points(scene.nrm_s, STATIC_NORMAL)
+        self.upload_octree(scene.oct_s, dynamic=False)
+        if scene.col_d is not None and len(scene.col_d):
+            self.upload_points(scene.col_d, DYNAMIC_COLOR)
+            self.upload_points(scene.nrm_d, DYNAMIC_NORMAL)
+        self.upload_octree(scene.oct_d, dynamic=True)
+
+    # ---- extensions ---------------------------------------------------------------
+    def sync(self):
+        self.lib.octree_cuc_sync(self._p)
+
+    def frame_size(self):
+        w, h = C.c_int(0), C.c_int(0)
+        self.lib.octree_cuc_frame_size(self._p, C.byref(w), C.byref(h))
+        return w.value, h.value
+
+    def read_frame(self, out=None, views=1):
+        """RGBA8 frame(s) as uint8 [views*H, W, 4], row 0 = bottom."""
+        w, h = self.frame_size()
+        if out is None:
+            out = np.empty((h * views, w, 4), dtype=np.uint8)
+        got = self.lib.octree_cuc_read_frame(self._p, out.ctypes.data_as(C.c_void_p), out.nbytes)
+        if got == 0:
+            raise RuntimeError("read_frame: no frame or buffer too small")
+        return out
+
+    def frame_device(self):
+        return int(self.lib.octree_cuc_frame_device(self._p))
+
+    def set_frame_target(self, device_ptr, pitch_pixels=0, keepalive=None):
+        self._keep = keepalive
+        self.lib.octree_cuc_set_frame_target(self._p, int(device_ptr), int(pitch_pixels))
+
+    def enable_aux(self, on=True):
+        self.lib.octree_cuc_enable_aux(self._p, int(bool(on)))
+
+    def read_aux(self, views=1):
+        w, h = self.frame_size()
+        flags = np.empty((h * views, w), dtype=np.uint8)
+        aux = np.empty((h * views, w, AUX_STRIDE), dtype=np.int32)
+        got = self.lib.octree_cuc_read_aux(self._p, flags.ctypes.data_as(C.c_void_p), aux.ctypes.data_as(C.c_void_p))
+        if got == 0:
+            raise RuntimeError("read_aux: aux planes are not enabled")
+        return flags, aux
+
+    def enable_counters(self, on=True):
+        self.lib.octree_cuc_enable_counters(self._p, int(bool(on)))
+
+    def read_counters(self):
+        c = Counters()
+        self.lib.octree_cuc_read_counters(self._p, C.byref(c))
+        return c.as_dict()
+
+    def set_shard(self, rank, world, tile_w=64, tile_h=64):
+        self.lib.octree_cuc_set_shard(self._p, int(rank), int(world), int(tile_w), int(tile_h))
+
+    def set_light(self, light):
+        if light is None:
+            self.lib.octree_cuc_set_light(self._p, None)
+        else:
+            arr = (C.c_float * 3)(*[float(v) for v in light])
+            self.lib.octree_cuc_set_light(self._p, C.cast(arr, C.c_void_p))
+
+    def set_kernel(self, which):
+        self.lib.octree_cuc_set_kernel(self._p, int(which))
+
+    def last_kernel(self):
+        return int(self.lib.octree_cuc_last_kernel(self._p))
+
+    def last_frame_ms(self):
+        return float(self.lib.octree_cuc_last_frame_ms(self._p))
+
+    def launch_count(self):
+        return int(self.lib.octree_cuc_launch_count(self._p))
+
+    def update_views(self, width, height, positions, angles, lighta=0.0, quality=10, maxlevel=12, basesize=1800.0,
+                     shoot=0):
+        pos = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
+        ang = np.ascontiguousarray(angles, dtype=np.float32).reshape(-1, 3)
+        assert pos.shape == ang.shape
+        self.lib.octree_cuc_update_views(self._p, pos.shape[0], float(width), float(height),
+                                         pos.ctypes.data_as(C.c_void_p), ang.ctypes.data_as(C.c_void_p),
+                                         float(lighta), int(quality), int(maxlevel), float(basesize), int(shoot))
+        return pos.shape[0]
+
+    def export_pending(self):
+        need = self.lib.octree_cuc_export_pending(self._p, None, 0)
+        buf = np.empty(need, dtype=np.uint8)
+        self.lib.octree_cuc_export_pending(self._p, buf.ctypes.data_as(C.c_void_p), need)
+        return buf
+
+    def apply_blob(self, blob):
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        self.lib.octree_cuc_apply_blob(self._p, blob.ctypes.data_as(C.c_void_p), blob.nbytes)
+
+    def destroy(self):
+        if self.rc.impl:
+            self.lib.octree_cuc_destroy(self._p)
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass

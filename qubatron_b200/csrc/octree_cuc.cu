@@ -1,0 +1,1013 @@
+// octree_cuc.cu -- the C-ABI connector (include/octree_cuc.h): device memory,
+// range uploads with on-device relayout, per-frame uniform set-up and kernel
+// launches.  Replaces /root/reference/src/qubatron/octree_glc.c.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo
+// (see qubatron_b200/csrc/Makefile).  No CPU fallback: every entry point that
+// needs the GPU aborts with a message if CUDA is unusable.
+#include "../../include/octree_cuc.h"
+
+#include "octree_render.cuh"
+#include "octree_trace_fast.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <vector>
+
+namespace
+{
+
+using namespace qb;
+
+#define CUDA_OK(call)                                                                                                 \
+    do                                                                                                                \
+    {                                                                                                                 \
+        cudaError_t e__ = (call);                                                                                     \
+        if (e__ != cudaSuccess)                                                                                       \
+        {                                                                                                             \
+            fprintf(stderr, "octree_cuc: CUDA error %s at %s:%d: %s\n", cudaGetErrorName(e__), __FILE__, __LINE__,    \
+                    cudaGetErrorString(e__));                                                                         \
+            abort();                                                                                                  \
+        }                                                                                                             \
+    } while (0)
+
+[[noreturn]] void die(const char* msg)
+{
+    fprintf(stderr, "octree_cuc: %s\n", msg);
+    abort();
+}
+
+// ---------------------------------------------------------------------------
+// relayout kernels: the host side speaks the reference's formats (12-int nodes,
+// float[3] points); the device arrays are the traversal layout of
+// octree_types.cuh.  Both kernels move 4-byte words.
+// ---------------------------------------------------------------------------
+
+// words [first_word, first_word + nwords) of a 12-int node array -> child/model
+__global__ void relayout_octree_kernel(const int* __restrict__ src, size_t first_word, size_t nwords,
+                                       int* __restrict__ child, int* __restrict__ model)
+{
+    size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+    if (i >= nwords) return;
+    size_t k    = first_word + i;
+    size_t node = k / 12;
+    int    slot = (int) (k - node * 12);
+    int    v    = src[i];
+    if (slot < 8)
+        child[node * 8 + slot] = v;
+    else if (slot == 8)
+        model[node] = v;
+}
+
+// words of a float[3] array -> 32-byte point records; which = 0 colour, 1 normal
+__global__ void relayout_points_kernel(const float* __restrict__ src, size_t first_word, size_t nwords,
+                                       float* __restrict__ rec, int which)
+{
+    size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+    if (i >= nwords) return;
+    size_t k                       = first_word + i;
+    size_t pt                      = k / 3;
+    int    c                       = (int) (k - pt * 3);
+    rec[pt * 8 + which * 4 + c]    = src[i];
+    if (c == 0) rec[pt * 8 + which * 4 + 3] = which ? 0.0f : 1.0f;
+}
+
+// batched small ranges ("zero-and-append" node uploads, modelutil.c L429-501):
+// one launch applies every pending range
+struct RangeDesc
+{
+    unsigned long long dst_word; // word offset in the logical (reference-format) array
+    unsigned int       src_word; // word offset in the packed payload
+    unsigned int       nwords;
+    int                buftype;
+    int                pad;
+};
+struct ScatterTargets
+{
+    int*   child[2];
+    int*   model[2];
+    float* rec[2];
+};
+__global__ void scatter_ranges_kernel(const RangeDesc* __restrict__ descs, int ndesc, const int* __restrict__ payload,
+                                      unsigned int total_words, ScatterTargets T)
+{
+    unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total_words) return;
+    int lo = 0, hi = ndesc - 1; // last descriptor with src_word <= i
+    while (lo < hi)
+    {
+        int mid = (lo + hi + 1) >> 1;
+        if (descs[mid].src_word <= i)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    const RangeDesc d = descs[lo];
+    size_t          k = d.dst_word + (i - d.src_word);
+    int             v = payload[i];
+    switch (d.buftype)
+    {
+        case OCTREE_GLC_BUFFER_STATIC_OCTREE:
+        case OCTREE_GLC_BUFFER_DYNAMIC_OCTREE:
+        {
+            int    t    = d.buftype == OCTREE_GLC_BUFFER_DYNAMIC_OCTREE;
+            size_t node = k / 12;
+            int    slot = (int) (k - node * 12);
+            if (slot < 8)
+                T.child[t][node * 8 + slot] = v;
+            else if (slot == 8)
+                T.model[t][node] = v;
+            break;
+        }
+        default:
+        {
+            int t     = (d.buftype == OCTREE_GLC_BUFFER_DYNAMIC_COLOR || d.buftype == OCTREE_GLC_BUFFER_DYNAMIC_NORMAL);
+            int which = (d.buftype == OCTREE_GLC_BUFFER_STATIC_NORMAL || d.buftype == OCTREE_GLC_BUFFER_DYNAMIC_NORMAL);
+            size_t pt = k / 3;
+            int    c  = (int) (k - pt * 3);
+            T.rec[t][pt * 8 + which * 4 + c] = __int_as_float(v);
+            if (c == 0) T.rec[t][pt * 8 + which * 4 + 3] = which ? 0.0f : 1.0f;
+            break;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// connector state
+// ---------------------------------------------------------------------------
+
+struct DevArray
+{
+    void*  ptr   = nullptr;
+    size_t bytes = 0;
+};
+
+struct Tree
+{
+    DevArray child; // 32 B per node
+    DevArray model; // 4 B per node
+    size_t   cap_nodes = 0;
+    size_t   nodes     = 0; // highest node uploaded + 1
+};
+struct Points
+{
+    DevArray rec; // 32 B per point
+    size_t   cap_points = 0;
+    size_t   points     = 0;
+};
+
+constexpr size_t STAGE_BYTES   = 64u << 20; // device staging chunk for bulk uploads
+constexpr size_t BATCH_BYTES   = 8u << 20;  // pinned staging for small ranges
+constexpr size_t BATCH_MAXDESC = 1u << 16;
+constexpr size_t SMALL_RANGE   = 256u << 10; // ranges up to this size are batched
+constexpr int    VIEW_RING     = 4;
+
+struct Impl
+{
+    int          device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
+    bool         timed = false;
+
+    Tree   tree[2];
+    Points pts[2];
+
+    void* stage_dev = nullptr; // STAGE_BYTES
+
+    // pending small ranges
+    char*                          batch_host = nullptr; // pinned, BATCH_BYTES
+    RangeDesc*                     desc_host  = nullptr; // pinned
+    void*                          batch_dev  = nullptr;
+    RangeDesc*                     desc_dev   = nullptr;
+    size_t                         batch_used = 0;
+    std::vector<RangeDesc>         descs;
+    std::map<unsigned long long, std::pair<unsigned long long, int>> intervals[6]; // start -> (end, desc index)
+
+    // frame
+    uchar4*             frame       = nullptr;
+    size_t              frame_cap   = 0; // pixels
+    uint64_t            ext_target  = 0;
+    size_t              ext_pitch   = 0;
+    uint8_t*            flags       = nullptr;
+    int*                aux         = nullptr;
+    size_t              aux_cap     = 0; // pixels
+    bool                aux_on      = false;
+    bool                count_on    = false;
+    unsigned long long* counters    = nullptr;
+    ViewParams*         views_host  = nullptr; // pinned
+    ViewParams*         views_dev   = nullptr;
+    int                 views_cap   = 0;
+    cudaEvent_t         slot_ev[VIEW_RING] = {};
+    bool                slot_used[VIEW_RING] = {};
+    uint64_t            frame_seq   = 0;
+    int                 W = 0, H = 0, n_views = 0;
+
+    int   shard_rank = 0, shard_world = 1, tile_w = 64, tile_h = 64;
+    bool  light_override = false;
+    float light[3]       = {0, 0, 0};
+    int   kernel_choice  = 0;
+    int   last_kernel    = 0;
+
+    uint64_t launches = 0;
+    uint64_t memsize  = 0;
+};
+
+int g_selected_device = -1;
+
+Impl* impl_of(octree_glc_t* rc)
+{
+    if (!rc || !rc->impl) die("connector used before octree_glc_init");
+    Impl* I = (Impl*) rc->impl;
+    CUDA_OK(cudaSetDevice(I->device));
+    return I;
+}
+
+void publish_memsize(octree_glc_t* rc, Impl* I)
+{
+    rc->memsize_bytes = I->memsize;
+    rc->memsize       = I->memsize > 0xffffffffull ? 0xffffffffu : (unsigned int) I->memsize;
+}
+
+void dev_alloc(Impl* I, DevArray& a, size_t bytes)
+{
+    CUDA_OK(cudaMalloc(&a.ptr, bytes));
+    CUDA_OK(cudaMemsetAsync(a.ptr, 0, bytes, I->stream));
+    a.bytes = bytes;
+    I->memsize += bytes;
+}
+void dev_free(Impl* I, DevArray& a)
+{
+    if (a.ptr)
+    {
+        CUDA_OK(cudaFree(a.ptr));
+        I->memsize -= a.bytes;
+    }
+    a.ptr   = nullptr;
+    a.bytes = 0;
+}
+// grow to `bytes`, keeping the old content, zero-filling the rest
+void dev_grow(Impl* I, DevArray& a, size_t bytes)
+{
+    DevArray n;
+    dev_alloc(I, n, bytes);
+    if (a.ptr)
+    {
+        CUDA_OK(cudaMemcpyAsync(n.ptr, a.ptr, a.bytes, cudaMemcpyDeviceToDevice, I->stream));
+        CUDA_OK(cudaStreamSynchronize(I->stream));
+        dev_free(I, a);
+    }
+    a = n;
+}
+
+size_t grown(size_t want) { return want + want / 4 + 4096; } // capacity policy: +25 %
+
+ScatterTargets scatter_targets(Impl* I)
+{
+    ScatterTargets T;
+    for (int t = 0; t < 2; t++)
+    {
+        T.child[t] = (int*) I->tree[t].child.ptr;
+        T.model[t] = (int*) I->tree[t].model.ptr;
+        T.rec[t]   = (float*) I->pts[t].rec.ptr;
+    }
+    return T;
+}
+
+void flush_pending(Impl* I)
+{
+    if (I->descs.empty()) return;
+    const size_t nd = I->descs.size();
+    memcpy(I->desc_host, I->descs.data(), nd * sizeof(RangeDesc));
+    CUDA_OK(cudaMemcpyAsync(I->batch_dev, I->batch_host, I->batch_used, cudaMemcpyHostToDevice, I->stream));
+    CUDA_OK(cudaMemcpyAsync(I->desc_dev, I->desc_host, nd * sizeof(RangeDesc), cudaMemcpyHostToDevice, I->stream));
+    unsigned int words = (unsigned int) (I->batch_used / 4);
+    scatter_ranges_kernel<<<(words + 255) / 256, 256, 0, I->stream>>>(I->desc_dev, (int) nd, (const int*) I->batch_dev,
+                                                                       words, scatter_targets(I));
+    CUDA_OK(cudaGetLastError());
+    I->launches++;
+    // the pinned staging is reused by the next batch
+    CUDA_OK(cudaStreamSynchronize(I->stream));
+    I->descs.clear();
+    I->batch_used = 0;
+    for (auto& m : I->intervals) m.clear();
+}
+
+bool is_octree(int buftype)
+{
+    return buftype == OCTREE_GLC_BUFFER_STATIC_OCTREE || buftype == OCTREE_GLC_BUFFER_DYNAMIC_OCTREE;
+}
+int tree_index(int buftype)
+{
+    return (buftype == OCTREE_GLC_BUFFER_DYNAMIC_COLOR || buftype == OCTREE_GLC_BUFFER_DYNAMIC_NORMAL ||
+            buftype == OCTREE_GLC_BUFFER_DYNAMIC_OCTREE)
+               ? 1
+               : 0;
+}
+
+// make sure the device arrays behind `buftype` hold `size` logical bytes;
+// returns true when they had to grow
+bool ensure_capacity(Impl* I, int buftype, size_t size)
+{
+    const int t = tree_index(buftype);
+    if (is_octree(buftype))
+    {
+        Tree&  T     = I->tree[t];
+        size_t nodes = (size + 47) / 48;
+        if (nodes <= T.cap_nodes) return false;
+        flush_pending(I);
+        size_t cap = grown(nodes);
+        dev_grow(I, T.child, cap * 32);
+        dev_grow(I, T.model, cap * 4);
+        T.cap_nodes = cap;
+        return true;
+    }
+    Points& Pn     = I->pts[t];
+    size_t  points = (size + 11) / 12;
+    if (points <= Pn.cap_points) return false;
+    flush_pending(I);
+    size_t cap = grown(points);
+    dev_grow(I, Pn.rec, cap * 32);
+    Pn.cap_points = cap;
+    return true;
+}
+
+void note_extent(Impl* I, int buftype, size_t end_byte)
+{
+    const int t = tree_index(buftype);
+    if (is_octree(buftype))
+    {
+        size_t n = (end_byte + 47) / 48;
+        if (n > I->tree[t].nodes) I->tree[t].nodes = n;
+    }
+    else
+    {
+        size_t n = (end_byte + 11) / 12;
+        if (n > I->pts[t].points) I->pts[t].points = n;
+    }
+}
+
+void upload_bulk(Impl* I, const char* data, int buftype, size_t s, size_t e)
+{
+    flush_pending(I);
+    const int t = tree_index(buftype);
+    for (size_t off = s; off < e; off += STAGE_BYTES)
+    {
+        size_t n = e - off < STAGE_BYTES ? e - off : STAGE_BYTES;
+        // pageable source: the call returns once `data` has been consumed
+        CUDA_OK(cudaMemcpyAsync(I->stage_dev, data + off, n, cudaMemcpyHostToDevice, I->stream));
+        size_t   words  = n / 4;
+        unsigned blocks = (unsigned) ((words + 255) / 256);
+        if (is_octree(buftype))
+            relayout_octree_kernel<<<blocks, 256, 0, I->stream>>>((const int*) I->stage_dev, off / 4, words,
+                                                                  (int*) I->tree[t].child.ptr,
+                                                                  (int*) I->tree[t].model.ptr);
+        else
+        {
+            int which = (buftype == OCTREE_GLC_BUFFER_STATIC_NORMAL || buftype == OCTREE_GLC_BUFFER_DYNAMIC_NORMAL);
+            relayout_points_kernel<<<blocks, 256, 0, I->stream>>>((const float*) I->stage_dev, off / 4, words,
+                                                                  (float*) I->pts[t].rec.ptr, which);
+        }
+        CUDA_OK(cudaGetLastError());
+        I->launches++;
+    }
+    // stage_dev is reused by the next call and `data` may be pageable: finish here
+    CUDA_OK(cudaStreamSynchronize(I->stream));
+}
+
+void upload_batched(Impl* I, const char* data, int buftype, size_t s, size_t e)
+{
+    const size_t bytes = e - s;
+    auto&        iv    = I->intervals[buftype];
+
+    // identical range uploaded again: newest payload wins, in place
+    auto same = iv.find(s);
+    if (same != iv.end() && same->second.first == e)
+    {
+        const RangeDesc& d = I->descs[same->second.second];
+        memcpy(I->batch_host + (size_t) d.src_word * 4, data + s, bytes);
+        return;
+    }
+    // a different, overlapping pending range: apply what is queued first so that
+    // ranges take effect in call order
+    bool overlap = false;
+    auto it      = iv.lower_bound(s);
+    if (it != iv.end() && it->first < e) overlap = true;
+    if (it != iv.begin())
+    {
+        auto pr = std::prev(it);
+        if (pr->second.first > s) overlap = true;
+    }
+    if (overlap || I->batch_used + bytes > BATCH_BYTES || I->descs.size() + 1 > BATCH_MAXDESC) flush_pending(I);
+
+    RangeDesc d;
+    d.dst_word = s / 4;
+    d.src_word = (unsigned int) (I->batch_used / 4);
+    d.nwords   = (unsigned int) (bytes / 4);
+    d.buftype  = buftype;
+    d.pad      = 0;
+    memcpy(I->batch_host + I->batch_used, data + s, bytes);
+    I->batch_used += bytes;
+    I->intervals[buftype][s] = std::make_pair((unsigned long long) e, (int) I->descs.size());
+    I->descs.push_back(d);
+}
+
+// smallest float d with acosf(d) < 0.02f: the host-libm form of the light-disc
+// test `camangle < 0.02` (octree_fsh.c L418, L452).  acosf is monotone over the
+// scanned interval (checked by tests/test_oracle.py::test_disc_threshold).
+float disc_dot_min()
+{
+    static float cached = 0.0f;
+    if (cached != 0.0f) return cached;
+    uint32_t lo, hi;
+    float    flo = 0.99f, fhi = 1.0f;
+    memcpy(&lo, &flo, 4);
+    memcpy(&hi, &fhi, 4);
+    while (lo < hi) // acosf(lo) >= 0.02 (false), acosf(hi) = 0 < 0.02 (true)
+    {
+        uint32_t mid = lo + (hi - lo) / 2;
+        float    fm;
+        memcpy(&fm, &mid, 4);
+        if (acosf(fm) < 0.02f)
+            hi = mid;
+        else
+            lo = mid + 1;
+    }
+    memcpy(&cached, &hi, 4);
+    return cached;
+}
+
+void host_cross(const float* a, const float* b, float* r)
+{
+    volatile float x = a[1] * b[2] - b[1] * a[2];
+    volatile float y = a[2] * b[0] - b[2] * a[0];
+    volatile float z = a[0] * b[1] - b[0] * a[1];
+    r[0] = x, r[1] = y, r[2] = z;
+}
+// octree_fsh.c L392-395 evaluated on the host in fp32 (per-frame constants)
+void host_quat_rotate(const float* q, const float* v, float* out)
+{
+    float c1[3], t[3], c2[3];
+    host_cross(q, v, c1);
+    for (int i = 0; i < 3; i++)
+    {
+        volatile float m = q[3] * v[i];
+        volatile float s = c1[i] + m;
+        t[i]             = s;
+    }
+    host_cross(q, t, c2);
+    for (int i = 0; i < 3; i++)
+    {
+        volatile float m = 2.0f * c2[i];
+        volatile float s = v[i] + m;
+        out[i]           = s;
+    }
+}
+void host_quat_axis_angle(const float* axis, float angle, float* q)
+{
+    volatile float half = angle * 0.5f;
+    float          sn = sinf(half), cs = cosf(half);
+    for (int i = 0; i < 3; i++)
+    {
+        volatile float m = axis[i] * sn;
+        q[i]             = m;
+    }
+    q[3] = cs;
+}
+
+// bits(m) + maxlevel <= 24 for basesize = m * 2^e, m odd: every cube corner and
+// centre k * basesize / 2^maxlevel is then exact in fp32, level sizes included
+bool grid_is_exact(float basesize, int maxlevel)
+{
+    if (!(basesize > 0.0f) || !std::isfinite(basesize) || maxlevel < 1 || maxlevel > 16) return false;
+    int   e;
+    float m  = frexpf(basesize, &e); // basesize = m * 2^e, 0.5 <= m < 1
+    uint32_t mi = (uint32_t) ldexpf(m, 24); // 24-bit integer mantissa
+    while (mi && !(mi & 1)) mi >>= 1;
+    int bits = 0;
+    while (mi >> bits) bits++;
+    if (bits + maxlevel > 23) return false;
+    return e - 24 - maxlevel > -120; // far from the subnormal range
+}
+
+void fill_view(Impl* I, ViewParams& V, float ow, const float* position, const float* angle, float lighta, int shoot)
+{
+    const float lightc[3] = {420.0f, 200.0f, 680.0f}; // octree_glc.c L91
+    V.camfp[0]            = position[0];
+    V.camfp[1]            = position[1];
+    V.camfp[2]            = position[2];
+    if (I->light_override)
+    {
+        V.light[0] = I->light[0];
+        V.light[1] = I->light[1];
+        V.light[2] = I->light[2];
+    }
+    else
+    {
+        // octree_glc.c L264: double arithmetic, rounded once on store
+        V.light[0] = lightc[0];
+        V.light[1] = (float) ((double) lightc[1] - (double) sinf(lighta) * 20.0);
+        V.light[2] = (float) ((double) lightc[2] - (double) sinf(lighta) * 200.0);
+    }
+    (void) ow;
+    const float yaxis[3] = {0.0f, 1.0f, 0.0f};
+    const float negx[3]  = {-1.0f, 0.0f, 0.0f};
+    float       vx[3];
+    host_quat_axis_angle(yaxis, -angle[0], V.qz); // octree_fsh.c L406-408
+    host_quat_rotate(V.qz, negx, vx);
+    host_quat_axis_angle(vx, -angle[1], V.qx);
+
+    float cl[3];
+    for (int i = 0; i < 3; i++)
+    {
+        volatile float d = V.light[i] - V.camfp[i];
+        cl[i]            = d;
+    }
+    volatile float xx = cl[0] * cl[0], yy = cl[1] * cl[1], zz = cl[2] * cl[2];
+    volatile float s1 = xx + yy;
+    volatile float s2 = s1 + zz;
+    float          l  = sqrtf(s2);
+    for (int i = 0; i < 3; i++)
+    {
+        volatile float q = cl[i] / l;
+        V.camlight_n[i]  = q;
+    }
+    V.disc_dot_min = disc_dot_min();
+    V.shoot        = shoot;
+}
+
+void launch_generic(Impl* I, const FrameParams& P, unsigned blocks)
+{
+    if (I->aux_on && I->count_on)
+        render_kernel<GenericTracer, true, true><<<blocks, BLOCK_THREADS, 0, I->stream>>>(P);
+    else if (I->aux_on)
+        render_kernel<GenericTracer, true, false><<<blocks, BLOCK_THREADS, 0, I->stream>>>(P);
+    else if (I->count_on)
+        render_kernel<GenericTracer, false, true><<<blocks, BLOCK_THREADS, 0, I->stream>>>(P);
+    else
+        render_kernel<GenericTracer, false, false><<<blocks, BLOCK_THREADS, 0, I->stream>>>(P);
+}
+
+template <bool DYN>
+void launch_fast_dyn(Impl* I, const FrameParams& P, unsigned blocks)
+{
+    const size_t smem = (size_t) 3 * P.maxlevel * BLOCK_THREADS * sizeof(int);
+    if (I->aux_on && I->count_on)
+        render_fast_kernel<DYN, true, true><<<blocks, BLOCK_THREADS, smem, I->stream>>>(P);
+    else if (I->aux_on)
+        render_fast_kernel<DYN, true, false><<<blocks, BLOCK_THREADS, smem, I->stream>>>(P);
+    else if (I->count_on)
+        render_fast_kernel<DYN, false, true><<<blocks, BLOCK_THREADS, smem, I->stream>>>(P);
+    else
+        render_fast_kernel<DYN, false, false><<<blocks, BLOCK_THREADS, smem, I->stream>>>(P);
+}
+
+void launch_fast(Impl* I, const FrameParams& P, unsigned blocks)
+{
+    // a dynamic tree that is only a root (octree_reset, octree.c L89-93) has no geometry
+    if (P.tree_d.nodes > 1)
+        launch_fast_dyn<true>(I, P, blocks);
+    else
+        launch_fast_dyn<false>(I, P, blocks);
+}
+
+void render_views(octree_glc_t* rc, int n, float width, float height, const float* positions, const float* angles,
+                  float lighta, uint8_t quality, int maxlevel, float basesize, int shoot)
+{
+    Impl* I = impl_of(rc);
+    if (n <= 0) return;
+    if (maxlevel < 0 || maxlevel > GENERIC_STACK - 1) die("maxlevel out of range (reference stack is 18 levels)");
+    flush_pending(I);
+
+    // octree_glc.c L268-269, L288
+    const float ow = (float) ((double) width / (6.0 - (double) (float) quality / 2.0));
+    const float oh = (float) ((double) height / (6.0 - (double) (float) quality / 2.0));
+    const int   W = (int) ow, H = (int) oh;
+    if (W <= 0 || H <= 0) return;
+    const size_t pixels = (size_t) W * H;
+
+    if (!I->ext_target && pixels * n > I->frame_cap)
+    {
+        if (I->frame)
+        {
+            CUDA_OK(cudaStreamSynchronize(I->stream));
+            CUDA_OK(cudaFree(I->frame));
+            I->memsize -= I->frame_cap * 4;
+        }
+        CUDA_OK(cudaMalloc(&I->frame, pixels * n * 4));
+        CUDA_OK(cudaMemsetAsync(I->frame, 0, pixels * n * 4, I->stream));
+        I->frame_cap = pixels * n;
+        I->memsize += I->frame_cap * 4;
+    }
+    if (I->aux_on && pixels * n > I->aux_cap)
+    {
+        if (I->flags)
+        {
+            CUDA_OK(cudaStreamSynchronize(I->stream));
+            CUDA_OK(cudaFree(I->flags));
+            CUDA_OK(cudaFree(I->aux));
+            I->memsize -= I->aux_cap * 25;
+        }
+        CUDA_OK(cudaMalloc(&I->flags, pixels * n));
+        CUDA_OK(cudaMalloc(&I->aux, pixels * n * 6 * sizeof(int)));
+        I->aux_cap = pixels * n;
+        I->memsize += I->aux_cap * 25;
+    }
+    if (n > I->views_cap)
+    {
+        if (I->views_host)
+        {
+            CUDA_OK(cudaStreamSynchronize(I->stream));
+            CUDA_OK(cudaFreeHost(I->views_host));
+            CUDA_OK(cudaFree(I->views_dev));
+        }
+        I->views_cap = n < 64 ? 64 : n;
+        CUDA_OK(cudaMallocHost(&I->views_host, VIEW_RING * I->views_cap * sizeof(ViewParams)));
+        CUDA_OK(cudaMalloc(&I->views_dev, VIEW_RING * I->views_cap * sizeof(ViewParams)));
+    }
+    // per-frame constants travel through a small ring of pinned slots so that
+    // queuing a frame never waits for the previous one
+    const int slot = (int) (I->frame_seq++ % VIEW_RING);
+    if (I->slot_used[slot]) CUDA_OK(cudaEventSynchronize(I->slot_ev[slot]));
+    ViewParams* const vh = I->views_host + (size_t) slot * I->views_cap;
+    ViewParams* const vd = I->views_dev + (size_t) slot * I->views_cap;
+
+    for (int v = 0; v < n; v++)
+    {
+        ViewParams& V = vh[v];
+        fill_view(I, V, ow, positions + 3 * v, angles + 3 * v, lighta, shoot);
+        // octree_fsh.c L403 (tan(PI/4.0) folds to 1.0f)
+        V.cfp[0] = ow / 2.0f;
+        V.cfp[1] = oh / 2.0f;
+        V.cfp[2] = (ow / 2.0f) / 1.0f;
+    }
+    CUDA_OK(cudaMemcpyAsync(vd, vh, n * sizeof(ViewParams), cudaMemcpyHostToDevice, I->stream));
+    CUDA_OK(cudaEventRecord(I->slot_ev[slot], I->stream));
+    I->slot_used[slot] = true;
+
+    FrameParams P;
+    memset(&P, 0, sizeof(P));
+    for (int t = 0; t < 2; t++)
+    {
+        TreeDev& T = t ? P.tree_d : P.tree_s;
+        T.child    = (const int4*) I->tree[t].child.ptr;
+        T.model    = (const int*) I->tree[t].model.ptr;
+        T.nodes    = (int) I->tree[t].nodes;
+        PointsDev& Q = t ? P.pts_d : P.pts_s;
+        Q.rec        = (const float4*) I->pts[t].rec.ptr;
+        Q.points     = (int) I->pts[t].points;
+    }
+    P.basecube[0] = 0.0f; // octree_glc.c L263
+    P.basecube[1] = basesize;
+    P.basecube[2] = basesize;
+    P.basecube[3] = basesize;
+    P.maxlevel    = maxlevel;
+    P.leaf_size   = ldexpf(basesize, -maxlevel);
+    P.W           = W;
+    P.H           = H;
+    P.sx          = ow / (float) W;
+    P.sy          = oh / (float) H;
+    if (I->ext_target)
+    {
+        P.frame       = (uchar4*) (uintptr_t) I->ext_target;
+        P.pitch       = I->ext_pitch ? I->ext_pitch : (size_t) W;
+        P.view_stride = P.pitch * H;
+    }
+    else
+    {
+        P.frame       = I->frame;
+        P.pitch       = W;
+        P.view_stride = pixels;
+    }
+    P.flags    = I->flags;
+    P.aux      = I->aux;
+    P.counters = I->counters;
+
+    P.tile_w            = I->tile_w;
+    P.tile_h            = I->tile_h;
+    P.tiles_x           = (W + P.tile_w - 1) / P.tile_w;
+    P.tiles_y           = (H + P.tile_h - 1) / P.tile_h;
+    P.rank              = I->shard_rank;
+    P.world             = I->shard_world;
+    P.blocks_per_tile_x = P.tile_w / BLOCK_W;
+    P.blocks_per_tile_y = P.tile_h / BLOCK_H;
+    const int tiles     = P.tiles_x * P.tiles_y;
+    P.tiles_mine        = tiles > P.rank ? (tiles - P.rank + P.world - 1) / P.world : 0;
+    P.views             = vd;
+    P.n_views           = n;
+
+    I->W       = W;
+    I->H       = H;
+    I->n_views = n;
+
+    if (I->count_on) CUDA_OK(cudaMemsetAsync(I->counters, 0, CNT_COUNT * sizeof(unsigned long long), I->stream));
+    // glClear(0,0,0,0) (octree_glc.c L289-290) needs no pass of its own: the
+    // kernel stores every pixel of the tiles it owns, discarded ones as (0,0,0,0)
+
+    const unsigned blocks = (unsigned) ((size_t) P.tiles_mine * P.blocks_per_tile_x * P.blocks_per_tile_y * n);
+    CUDA_OK(cudaEventRecord(I->ev0, I->stream));
+    if (blocks)
+    {
+        bool fast = I->kernel_choice == 2 || (I->kernel_choice == 0 && grid_is_exact(basesize, maxlevel));
+        if (fast && !grid_is_exact(basesize, maxlevel)) die("fast kernel requested for a base cube that is not exact");
+        if (fast)
+            launch_fast(I, P, blocks);
+        else
+            launch_generic(I, P, blocks);
+        CUDA_OK(cudaGetLastError());
+        I->launches++;
+        I->last_kernel = fast ? 2 : 1;
+    }
+    CUDA_OK(cudaEventRecord(I->ev1, I->stream));
+    I->timed = true;
+    publish_memsize(rc, I);
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+
+extern "C" {
+
+const char* octree_cuc_version(void) { return "octree_cuc 0.1 (sm_100a)"; }
+
+void octree_cuc_select_device(int device) { g_selected_device = device; }
+
+octree_glc_t octree_glc_init(char* path)
+{
+    (void) path; // shader directory of the GL connector: kernels are built in
+    octree_glc_t rc;
+    memset(&rc, 0, sizeof(rc));
+
+    int         ndev = 0;
+    cudaError_t e    = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+    {
+        fprintf(stderr, "octree_cuc: no usable CUDA device (%s); this connector has no CPU path\n",
+                cudaGetErrorString(e));
+        abort();
+    }
+    Impl* I = new Impl();
+    if (g_selected_device >= 0)
+        I->device = g_selected_device;
+    else
+        CUDA_OK(cudaGetDevice(&I->device));
+    CUDA_OK(cudaSetDevice(I->device));
+    CUDA_OK(cudaStreamCreateWithFlags(&I->stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaEventCreate(&I->ev0));
+    CUDA_OK(cudaEventCreate(&I->ev1));
+    for (int i = 0; i < VIEW_RING; i++) CUDA_OK(cudaEventCreateWithFlags(&I->slot_ev[i], cudaEventDisableTiming));
+    CUDA_OK(cudaMalloc(&I->stage_dev, STAGE_BYTES));
+    CUDA_OK(cudaMalloc(&I->batch_dev, BATCH_BYTES));
+    CUDA_OK(cudaMalloc(&I->desc_dev, BATCH_MAXDESC * sizeof(RangeDesc)));
+    CUDA_OK(cudaMallocHost(&I->batch_host, BATCH_BYTES));
+    CUDA_OK(cudaMallocHost(&I->desc_host, BATCH_MAXDESC * sizeof(RangeDesc)));
+    CUDA_OK(cudaMalloc(&I->counters, CNT_COUNT * sizeof(unsigned long long)));
+    CUDA_OK(cudaMemset(I->counters, 0, CNT_COUNT * sizeof(unsigned long long)));
+    I->memsize = STAGE_BYTES + BATCH_BYTES + BATCH_MAXDESC * sizeof(RangeDesc);
+    // every tree has a root (octree.c L63): node 0 reads as "no children" until uploaded
+    for (int t = 0; t < 2; t++)
+    {
+        ensure_capacity(I, t ? OCTREE_GLC_BUFFER_DYNAMIC_OCTREE : OCTREE_GLC_BUFFER_STATIC_OCTREE, 48);
+        ensure_capacity(I, t ? OCTREE_GLC_BUFFER_DYNAMIC_COLOR : OCTREE_GLC_BUFFER_STATIC_COLOR, 12);
+    }
+    CUDA_OK(cudaStreamSynchronize(I->stream));
+    rc.impl = I;
+    publish_memsize(&rc, I);
+    return rc;
+}
+
+void octree_cuc_destroy(octree_glc_t* rc)
+{
+    if (!rc || !rc->impl) return;
+    Impl* I = impl_of(rc);
+    CUDA_OK(cudaStreamSynchronize(I->stream));
+    for (int t = 0; t < 2; t++)
+    {
+        dev_free(I, I->tree[t].child);
+        dev_free(I, I->tree[t].model);
+        dev_free(I, I->pts[t].rec);
+    }
+    cudaFree(I->stage_dev);
+    cudaFree(I->batch_dev);
+    cudaFree(I->desc_dev);
+    cudaFreeHost(I->batch_host);
+    cudaFreeHost(I->desc_host);
+    cudaFree(I->counters);
+    if (I->frame) cudaFree(I->frame);
+    if (I->flags) cudaFree(I->flags);
+    if (I->aux) cudaFree(I->aux);
+    if (I->views_host) cudaFreeHost(I->views_host);
+    if (I->views_dev) cudaFree(I->views_dev);
+    for (int i = 0; i < VIEW_RING; i++) cudaEventDestroy(I->slot_ev[i]);
+    cudaEventDestroy(I->ev0);
+    cudaEventDestroy(I->ev1);
+    cudaStreamDestroy(I->stream);
+    delete I;
+    rc->impl          = nullptr;
+    rc->memsize       = 0;
+    rc->memsize_bytes = 0;
+}
+
+void octree_glc_upload_texbuffer_data(octree_glc_t* rc, void* data, int type, size_t size, size_t itemsize,
+                                      size_t start, size_t end, octree_glc_buffer_t buftype)
+{
+    Impl* I = impl_of(rc);
+    if ((int) buftype < 0 || (int) buftype > 5) die("upload: unknown buffer type");
+    if (itemsize == 0 || data == nullptr) return;
+    const bool oct = is_octree(buftype);
+    if (oct && (type != OCTREE_CUC_GL_INT || itemsize != 16)) die("upload: octree buffers take GL_INT items of 16 bytes");
+    if (!oct && (type != OCTREE_CUC_GL_FLOAT || itemsize != 12))
+        die("upload: colour/normal buffers take GL_FLOAT items of 12 bytes");
+
+    // octree_glc.c L412-428: growth re-uploads the whole array
+    if (ensure_capacity(I, buftype, size))
+    {
+        start = 0;
+        end   = size;
+    }
+    // octree_glc.c L432-433: texel granularity, rounded down
+    size_t s = (start / itemsize) * itemsize;
+    size_t e = (end / itemsize) * itemsize;
+    if (e > (size / itemsize) * itemsize) e = (size / itemsize) * itemsize;
+    if (e > s)
+    {
+        note_extent(I, buftype, e);
+        if (e - s <= SMALL_RANGE)
+            upload_batched(I, (const char*) data, buftype, s, e);
+        else
+            upload_bulk(I, (const char*) data, buftype, s, e);
+    }
+    publish_memsize(rc, I);
+}
+
+void octree_glc_update(octree_glc_t* rc, float width, float height, v3_t position, v3_t angle, float lighta,
+                       uint8_t quality, int maxlevel, float basesize, int shoot)
+{
+    const float pos[3] = {position.x, position.y, position.z};
+    const float ang[3] = {angle.x, angle.y, angle.z};
+    render_views(rc, 1, width, height, pos, ang, lighta, quality, maxlevel, basesize, shoot);
+}
+
+void octree_cuc_update_views(octree_glc_t* rc, int n, float width, float height, const float* positions,
+                             const float* angles, float lighta, uint8_t quality, int maxlevel, float basesize,
+                             int shoot)
+{
+    render_views(rc, n, width, height, positions, angles, lighta, quality, maxlevel, basesize, shoot);
+}
+
+void octree_cuc_sync(octree_glc_t* rc)
+{
+    Impl* I = impl_of(rc);
+    flush_pending(I);
+    CUDA_OK(cudaStreamSynchronize(I->stream));
+}
+
+void octree_cuc_frame_size(octree_glc_t* rc, int* width, int* height)
+{
+    Impl* I = impl_of(rc);
+    if (width) *width = I->W;
+    if (height) *height = I->H;
+}
+
+size_t octree_cuc_read_frame(octree_glc_t* rc, uint8_t* rgba_host, size_t capacity)
+{
+    Impl*  I     = impl_of(rc);
+    size_t bytes = (size_t) I->W * I->H * 4 * (I->n_views ? I->n_views : 1);
+    if (I->ext_target) die("read_frame: frame target is external, read it there");
+    if (bytes == 0 || capacity < bytes) return 0;
+    CUDA_OK(cudaMemcpyAsync(rgba_host, I->frame, bytes, cudaMemcpyDeviceToHost, I->stream));
+    CUDA_OK(cudaStreamSynchronize(I->stream));
+    return bytes;
+}
+
+uint64_t octree_cuc_frame_device(octree_glc_t* rc)
+{
+    Impl* I = impl_of(rc);
+    return I->ext_target ? I->ext_target : (uint64_t) (uintptr_t) I->frame;
+}
+
+void octree_cuc_set_frame_target(octree_glc_t* rc, uint64_t device_ptr, size_t pitch_pixels)
+{
+    Impl* I       = impl_of(rc);
+    I->ext_target = device_ptr;
+    I->ext_pitch  = pitch_pixels;
+}
+
+void octree_cuc_enable_aux(octree_glc_t* rc, int enable) { impl_of(rc)->aux_on = enable != 0; }
+
+size_t octree_cuc_read_aux(octree_glc_t* rc, uint8_t* flags_host, int32_t* aux_host)
+{
+    Impl*  I      = impl_of(rc);
+    size_t pixels = (size_t) I->W * I->H * (I->n_views ? I->n_views : 1);
+    if (!I->aux_on || !I->flags || pixels == 0) return 0;
+    if (flags_host) CUDA_OK(cudaMemcpyAsync(flags_host, I->flags, pixels, cudaMemcpyDeviceToHost, I->stream));
+    if (aux_host)
+        CUDA_OK(cudaMemcpyAsync(aux_host, I->aux, pixels * 6 * sizeof(int), cudaMemcpyDeviceToHost, I->stream));
+    CUDA_OK(cudaStreamSynchronize(I->stream));
+    return pixels;
+}
+
+void octree_cuc_enable_counters(octree_glc_t* rc, int enable) { impl_of(rc)->count_on = enable != 0; }
+
+void octree_cuc_read_counters(octree_glc_t* rc, octree_cuc_counters* out)
+{
+    Impl*              I = impl_of(rc);
+    unsigned long long h[CNT_COUNT];
+    CUDA_OK(cudaMemcpyAsync(h, I->counters, sizeof(h), cudaMemcpyDeviceToHost, I->stream));
+    CUDA_OK(cudaStreamSynchronize(I->stream));
+    out->rays_primary = (int64_t) h[CNT_RAYS_PRIMARY];
+    out->rays_shadow  = (int64_t) h[CNT_RAYS_SHADOW];
+    out->rays_disc    = (int64_t) h[CNT_RAYS_DISC];
+    out->expand_s     = (int64_t) h[CNT_EXPAND_S];
+    out->expand_d     = (int64_t) h[CNT_EXPAND_D];
+    out->leaf_s       = (int64_t) h[CNT_LEAF_S];
+    out->leaf_d       = (int64_t) h[CNT_LEAF_D];
+    out->hits         = (int64_t) h[CNT_HITS];
+    out->discards     = (int64_t) h[CNT_DISCARDS];
+    out->descents     = (int64_t) h[CNT_DESCENTS];
+}
+
+void octree_cuc_set_shard(octree_glc_t* rc, int rank, int world, int tile_w, int tile_h)
+{
+    Impl* I = impl_of(rc);
+    if (world < 1 || rank < 0 || rank >= world) die("set_shard: need 0 <= rank < world");
+    if (tile_w <= 0 || tile_h <= 0 || tile_w % BLOCK_W || tile_h % BLOCK_H)
+        die("set_shard: tile size must be a multiple of 16 x 8 pixels");
+    I->shard_rank  = rank;
+    I->shard_world = world;
+    I->tile_w      = tile_w;
+    I->tile_h      = tile_h;
+}
+
+void octree_cuc_set_light(octree_glc_t* rc, const float* light)
+{
+    Impl* I           = impl_of(rc);
+    I->light_override = light != nullptr;
+    if (light) memcpy(I->light, light, sizeof(I->light));
+}
+
+void octree_cuc_set_kernel(octree_glc_t* rc, int which)
+{
+    if (which < 0 || which > 2) die("set_kernel: 0 auto, 1 generic, 2 fast");
+    impl_of(rc)->kernel_choice = which;
+}
+
+int octree_cuc_last_kernel(octree_glc_t* rc) { return impl_of(rc)->last_kernel; }
+
+float octree_cuc_last_frame_ms(octree_glc_t* rc)
+{
+    Impl* I = impl_of(rc);
+    if (!I->timed) return 0.0f;
+    CUDA_OK(cudaEventSynchronize(I->ev1));
+    float ms = 0.0f;
+    CUDA_OK(cudaEventElapsedTime(&ms, I->ev0, I->ev1));
+    return ms;
+}
+
+uint64_t octree_cuc_launch_count(octree_glc_t* rc) { return impl_of(rc)->launches; }
+
+// blob = { uint64 ndesc, uint64 payload_bytes, RangeDesc[ndesc], payload }
+size_t octree_cuc_export_pending(octree_glc_t* rc, void* blob_host, size_t capacity)
+{
+    Impl*  I    = impl_of(rc);
+    size_t nd   = I->descs.size();
+    size_t need = 16 + nd * sizeof(RangeDesc) + I->batch_used;
+    if (blob_host == nullptr || capacity < need) return need;
+    uint64_t hdr[2] = {(uint64_t) nd, (uint64_t) I->batch_used};
+    char*    p      = (char*) blob_host;
+    memcpy(p, hdr, 16);
+    memcpy(p + 16, I->descs.data(), nd * sizeof(RangeDesc));
+    memcpy(p + 16 + nd * sizeof(RangeDesc), I->batch_host, I->batch_used);
+    return need;
+}
+
+void octree_cuc_apply_blob(octree_glc_t* rc, const void* blob_host, size_t bytes)
+{
+    Impl* I = impl_of(rc);
+    if (bytes < 16) return;
+    const char* p = (const char*) blob_host;
+    uint64_t    hdr[2];
+    memcpy(hdr, p, 16);
+    if (16 + hdr[0] * sizeof(RangeDesc) + hdr[1] != bytes) die("apply_blob: malformed blob");
+    const RangeDesc* d       = (const RangeDesc*) (p + 16);
+    const char*      payload = p + 16 + hdr[0] * sizeof(RangeDesc);
+    for (uint64_t i = 0; i < hdr[0]; i++)
+    {
+        // re-enter through the batched path: `fake` is positioned so that
+        // fake + dst offset addresses this range's payload
+        size_t      s    = (size_t) d[i].dst_word * 4;
+        size_t      e    = s + (size_t) d[i].nwords * 4;
+        const char* fake = payload + (size_t) d[i].src_word * 4 - s;
+        ensure_capacity(I, d[i].buftype, e);
+        note_extent(I, d[i].buftype, e);
+        upload_batched(I, fake, d[i].buftype, s, e);
+    }
+    publish_memsize(rc, I);
+}
+
+} // extern "C"

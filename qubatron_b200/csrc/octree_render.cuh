@@ -1,0 +1,237 @@
+// octree_render.cuh -- the per-pixel program: camera ray, primary trace, shadow
+// ray from the light, shading, light disc, RGBA8 store.  One launch does the
+// whole frame (or this rank's tiles of it); traces are a template policy so the
+// generic and the register-stack traversal share everything else.
+//
+// Behaviour to reproduce: /root/reference/src/qubatron/shaders/octree_fsh.c
+// main() L399-464 and octree_vsh.c L11 (coord = pixel centre).
+// Compiled with -fmad=false (see octree_trace_generic.cuh).
+#pragma once
+#include "octree_trace_generic.cuh"
+
+namespace qb
+{
+
+__device__ __forceinline__ float3 cross3(float3 a, float3 b)
+{
+    return make_float3(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y);
+}
+__device__ __forceinline__ float dot3(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float3 normalize3(float3 a)
+{
+    float l = sqrtf(dot3(a, a));
+    return make_float3(a.x / l, a.y / l, a.z / l);
+}
+// octree_fsh.c L392-395
+__device__ __forceinline__ float3 quat_rotate(const float* q, float3 v)
+{
+    float3 qv = make_float3(q[0], q[1], q[2]);
+    float3 c1 = cross3(qv, v);
+    float3 t  = make_float3(c1.x + q[3] * v.x, c1.y + q[3] * v.y, c1.z + q[3] * v.z);
+    float3 c2 = cross3(qv, t);
+    return make_float3(v.x + 2.0f * c2.x, v.y + 2.0f * c2.y, v.z + 2.0f * c2.z);
+}
+__device__ __forceinline__ float max0(float a) { return a > 0.0f ? a : 0.0f; }
+__device__ __forceinline__ unsigned int unorm8(float v)
+{
+    if (!(v > 0.0f)) return 0u;
+    if (v > 1.0f) v = 1.0f;
+    return (unsigned int) __float2int_rn(v * 255.0f);
+}
+
+struct GenericTracer
+{
+    template <bool COUNT>
+    static __device__ __forceinline__ TraceResult trace(const FrameParams& P, float3 pos, float3 dir, RayCounters& c)
+    {
+        return trace_generic<COUNT>(P, pos, dir, c);
+    }
+};
+
+// pixel of thread `tid` inside the CTA's 16x8 block: each warp covers an 8x4
+// patch (lanes row-major inside it) so the 32 rays of a warp stay coherent
+__device__ __forceinline__ void block_pixel(int tid, int& lx, int& ly)
+{
+    int warp = tid >> 5, lane = tid & 31;
+    lx       = ((warp & 1) << 3) | (lane & 7);
+    ly       = ((warp >> 1) << 2) | (lane >> 3);
+}
+
+template <class TRACER, bool AUX, bool COUNT>
+__global__ void __launch_bounds__(BLOCK_THREADS) render_kernel(const FrameParams P)
+{
+    // CTA -> (view, shard tile, block inside the tile)
+    const int blocks_per_tile = P.blocks_per_tile_x * P.blocks_per_tile_y;
+    int       b               = blockIdx.x;
+    const int sub             = b % blocks_per_tile;
+    b /= blocks_per_tile;
+    const int tile_local = b % P.tiles_mine;
+    const int view       = b / P.tiles_mine;
+    const int tile       = P.rank + tile_local * P.world;
+    const int ty = tile / P.tiles_x, tx = tile - ty * P.tiles_x;
+    const int by = sub / P.blocks_per_tile_x, bx = sub - by * P.blocks_per_tile_x;
+
+    int lx, ly;
+    block_pixel(threadIdx.x, lx, ly);
+    const int px = tx * P.tile_w + bx * BLOCK_W + lx;
+    const int py = ty * P.tile_h + by * BLOCK_H + ly;
+
+    RayCounters cnt;
+    if (COUNT)
+    {
+#pragma unroll
+        for (int i = 0; i < CNT_COUNT; i++) cnt.v[i] = 0;
+    }
+
+    const bool active = px < P.W && py < P.H;
+    if (active)
+    {
+        const ViewParams& V = P.views[view];
+
+        const float3 camfp = make_float3(V.camfp[0], V.camfp[1], V.camfp[2]);
+        const float3 light = make_float3(V.light[0], V.light[1], V.light[2]);
+
+        // L402-404, L412-413
+        float3 csv = make_float3(((float) px + 0.5f) * P.sx - V.cfp[0], ((float) py + 0.5f) * P.sy - V.cfp[1],
+                                 0.0f - V.cfp[2]);
+        csv        = quat_rotate(V.qz, csv);
+        csv        = quat_rotate(V.qx, csv);
+
+        // L417-418; acos(d) < 0.02 is evaluated as d >= disc_dot_min (host libm threshold)
+        const float3 csv_n  = normalize3(csv);
+        const float  camdot = dot3(make_float3(V.camlight_n[0], V.camlight_n[1], V.camlight_n[2]), csv_n);
+        const bool   disc   = camdot >= V.disc_dot_min && camdot <= 1.0f;
+
+        int   flags   = 0;
+        bool  discard = false;
+        float cr = 0.f, cg = 0.f, cb = 0.f, ca = 0.f;
+        int   a0 = -1, a1 = -1, a2 = -1, a3 = -1, a4 = -1, a5 = -1;
+
+        if (COUNT) cnt.v[CNT_RAYS_PRIMARY]++;
+        TraceResult res = TRACER::template trace<COUNT>(P, camfp, csv, cnt);
+        if (res.status < 0) discard = true;
+
+        if (!discard && res.status == 1)
+        {
+            flags |= 2;
+            a0 = res.model_s;
+            a1 = res.model_d;
+            a2 = res.node_s;
+            a3 = res.node_d;
+
+            // L226-241: static point `model_s` (point 0 when the leaf is dynamic
+            // only), overridden by the dynamic point iff model_d > 0
+            const PointsDev& pts = (res.model_d > 0) ? P.pts_d : P.pts_s;
+            const int        idx = (res.model_d > 0) ? res.model_d : res.model_s;
+            float4           col = make_float4(0.f, 0.f, 0.f, 1.f), nrm = make_float4(0.f, 0.f, 0.f, 1.f);
+            if ((unsigned) idx < (unsigned) pts.points)
+            {
+                col = __ldg(pts.rec + 2 * (size_t) idx);
+                nrm = __ldg(pts.rec + 2 * (size_t) idx + 1);
+            }
+            cr = col.x;
+            cg = col.y;
+            cb = col.z;
+            ca = 1.0f;
+
+            if (res.iw > 0.0f) // L424-450
+            {
+                flags |= 4;
+                if (COUNT)
+                {
+                    cnt.v[CNT_HITS]++;
+                    cnt.v[CNT_RAYS_SHADOW]++;
+                }
+                const float3 lghtv = make_float3(res.ix - light.x, res.iy - light.y, res.iz - light.z);
+                TraceResult  lc    = TRACER::template trace<COUNT>(P, light, lghtv, cnt);
+                if (lc.status < 0)
+                    discard = true;
+                else
+                {
+                    if (lc.status == 1)
+                    {
+                        a4 = lc.node_s;
+                        a5 = lc.node_d;
+                    }
+                    const float dx = lc.ix - res.ix, dy = lc.iy - res.iy, dz = lc.iz - res.iz;
+                    const float sqr = dx * dx + dy * dy + dz * dz;
+
+                    const float3 nn  = normalize3(make_float3(nrm.x, nrm.y, nrm.z));
+                    const float3 nl  = normalize3(make_float3(-lghtv.x, -lghtv.y, -lghtv.z));
+                    const float3 nc  = normalize3(make_float3(-csv.x, -csv.y, -csv.z));
+                    const float  lna = max0(dot3(nl, nn));
+                    const float  cna = max0(dot3(nc, nn));
+                    const float  vis = (15.0f < sqr) ? 0.0f : 1.0f; // step(sqr, 15.0)
+                    if (vis != 0.0f) flags |= 8;
+
+                    const float f = 0.1f + 0.2f * cna + lna * vis * 0.7f;
+                    cr            = cr * f;
+                    cg            = cg * f;
+                    cb            = cb * f;
+                    cb *= 0.7f;
+                    const float g = (float) V.shoot * cna * 0.1f;
+                    cr += g;
+                    cg += g;
+                    cb += g;
+                }
+            }
+        }
+
+        if (!discard && disc) // L452-459
+        {
+            flags |= 16;
+            if (COUNT) cnt.v[CNT_RAYS_DISC]++;
+            const float3 lghtv = make_float3(light.x - camfp.x, light.y - camfp.y, light.z - camfp.z);
+            TraceResult  lc    = TRACER::template trace<COUNT>(P, camfp, lghtv, cnt);
+            if (lc.status < 0)
+                discard = true;
+            else
+            {
+                const float resvx = lc.ix - camfp.x;
+                if (resvx / lghtv.x > 1.0f)
+                {
+                    flags |= 32;
+                    cr = cg = cb = ca = 1.0f;
+                }
+            }
+        }
+
+        if (discard)
+        {
+            flags = 1;
+            a0 = a1 = a2 = a3 = a4 = a5 = -1;
+            cr = cg = cb = ca = 0.0f;
+            if (COUNT) cnt.v[CNT_DISCARDS]++;
+        }
+
+        const size_t p = (size_t) view * P.view_stride + (size_t) py * P.pitch + px;
+        P.frame[p]     = make_uchar4((unsigned char) unorm8(cr), (unsigned char) unorm8(cg), (unsigned char) unorm8(cb),
+                                     (unsigned char) unorm8(ca));
+        if (AUX)
+        {
+            const size_t q = (size_t) view * P.W * P.H + (size_t) py * P.W + px;
+            P.flags[q]     = (uint8_t) flags;
+            int* a         = P.aux + q * 6;
+            a[0]           = a0;
+            a[1]           = a1;
+            a[2]           = a2;
+            a[3]           = a3;
+            a[4]           = a4;
+            a[5]           = a5;
+        }
+    }
+
+    if (COUNT)
+    {
+#pragma unroll
+        for (int i = 0; i < CNT_COUNT; i++)
+        {
+            unsigned int v = cnt.v[i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if ((threadIdx.x & 31) == 0 && v) atomicAdd(P.counters + i, (unsigned long long) v);
+        }
+    }
+}
+
+} // namespace qb

@@ -1,0 +1,98 @@
+// octree_types.cuh -- device-side data layout and per-frame parameter block.
+//
+// HBM layout (see DESIGN.md "Data layout"):
+//   child_{s,d} : int4[2*nodes]  -- the 8 child indices of a node, 32 B, one
+//                                   aligned sector per node expansion
+//                                   (reference node = int32[12], octree.c L11-14)
+//   model_{s,d} : int32[nodes]   -- oct[8] of the node (point index), split out
+//                                   as the reference author wanted
+//                                   (octree_fsh.c L125)
+//   pts_{s,d}   : float4[2*pts]  -- {colour rgb, 1}, {normal xyz, 0}: one 32 B
+//                                   record per point (model.c L14-25 keeps two
+//                                   float[3] arrays)
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace qb
+{
+
+struct TreeDev
+{
+    const int4* child; // 2 x int4 per node
+    const int*  model; // oct[8] per node
+    int         nodes; // nodes uploaded so far (reads beyond return 0)
+};
+
+struct PointsDev
+{
+    const float4* rec; // 2 x float4 per point
+    int           points;
+};
+
+// work counters, same order as octree_cuc_counters
+enum
+{
+    CNT_RAYS_PRIMARY = 0,
+    CNT_RAYS_SHADOW,
+    CNT_RAYS_DISC,
+    CNT_EXPAND_S,
+    CNT_EXPAND_D,
+    CNT_LEAF_S,
+    CNT_LEAF_D,
+    CNT_HITS,
+    CNT_DISCARDS,
+    CNT_DESCENTS,
+    CNT_COUNT
+};
+
+// one view: everything main() of octree_fsh.c derives from the uniforms that is
+// constant over the frame, computed on the host in fp32
+struct ViewParams
+{
+    float camfp[3];
+    float light[3];
+    float qz[4];         // octree_fsh.c L406
+    float qx[4];         // L408
+    float cfp[3];        // L403
+    float camlight_n[3]; // normalize(light - camfp), L417-418
+    float disc_dot_min;  // smallest dot with acosf(dot) < 0.02f (L452), host libm
+    int   shoot;
+};
+
+struct FrameParams
+{
+    TreeDev   tree_s, tree_d;
+    PointsDev pts_s, pts_d;
+
+    float basecube[4]; // (0, S, S, S), octree_glc.c L263
+    int   maxlevel;
+    float leaf_size;   // S / 2^maxlevel (fast kernel, exact-grid mode)
+
+    int   W, H;   // viewport in pixels
+    float sx, sy; // coord scale = ow / W (1.0 for whole-number render sizes)
+
+    // outputs
+    uchar4*             frame;        // RGBA8, row 0 = bottom
+    size_t              pitch;        // pixels per row
+    size_t              view_stride;  // pixels between views of a batch
+    uint8_t*            flags;        // optional parity planes
+    int*                aux;
+    unsigned long long* counters;
+
+    // image-tile sharding
+    int tile_w, tile_h, tiles_x, tiles_y;
+    int rank, world;
+    int blocks_per_tile_x, blocks_per_tile_y;
+    int tiles_mine; // number of tiles this rank renders per view
+
+    // views
+    const ViewParams* views; // device array, n_views entries
+    int               n_views;
+};
+
+constexpr int BLOCK_W       = 16; // pixels per CTA in x
+constexpr int BLOCK_H       = 8;  // pixels per CTA in y
+constexpr int BLOCK_THREADS = BLOCK_W * BLOCK_H;
+
+} // namespace qb
