@@ -189,6 +189,23 @@ void octree_cuc_update_views(octree_glc_t* rc, int n, float width, float height,
                              const float* angles, float lighta, uint8_t quality, int maxlevel, float basesize,
                              int shoot);
 
+/* run all of the connector's work (uploads, kernels, copies) on a caller-owned
+ * CUDA stream, e.g. torch's current stream, so that collectives and event
+ * timing issued by the caller order naturally with the frames; 0 restores the
+ * connector's own stream. */
+void octree_cuc_set_stream(octree_glc_t* rc, uint64_t cuda_stream);
+
+/* allocate the internal framebuffer for `views` frames of width x height now
+ * (normally done lazily by the first update) */
+void octree_cuc_reserve_frame(octree_glc_t* rc, int width, int height, int views);
+
+/* fused tile gather over NVLink: rank 0 exports its framebuffer as a 64-byte
+ * CUDA IPC handle, the other ranks open it and render their tiles straight
+ * into it with peer stores (octree_cuc_set_frame_target). */
+void     octree_cuc_ipc_export_frame(octree_glc_t* rc, uint8_t* handle64);
+uint64_t octree_cuc_ipc_open(octree_glc_t* rc, const uint8_t* handle64);
+void     octree_cuc_ipc_close(octree_glc_t* rc, uint64_t device_ptr);
+
 /* multi-GPU range updates: pending ranges can be exported as one packed blob
  * (header + payload) by the rank that received the host uploads, broadcast by
  * the caller (NCCL), and applied on every other rank. */

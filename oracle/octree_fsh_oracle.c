@@ -686,7 +686,7 @@ void qb_oracle_trace_batch(const qb_scene* sc, const qb_uniforms* u, int64_t n, 
 #else
     threads = 1;
 #endif
-#pragma omp parallel for schedule(dynamic, 1024) num_threads(threads)
+#pragma omp parallel for schedule(dynamic, 64) num_threads(threads)
     for (int64_t i = 0; i < n; i++)
     {
         result[i] = qb_oracle_trace(sc, u, pos + i * 3, dir + i * 3, isp ? isp + i * 4 : NULL, NULL,

@@ -82,7 +82,7 @@ void qbref_trace_batch(octree_t* t, int64_t n, const float* pos, const float* di
 #else
     threads = 1;
 #endif
-#pragma omp parallel for schedule(dynamic, 1024) num_threads(threads)
+#pragma omp parallel for schedule(dynamic, 64) num_threads(threads)
     for (int64_t i = 0; i < n; i++)
     {
         v4_t tlf     = {0};

@@ -72,6 +72,11 @@ _PROTOS = {
     "octree_cuc_launch_count": (C.c_uint64, [C.POINTER(octree_glc_t)]),
     "octree_cuc_update_views": (None, [C.POINTER(octree_glc_t), C.c_int, C.c_float, C.c_float, C.c_void_p,
                                        C.c_void_p, C.c_float, C.c_uint8, C.c_int, C.c_float, C.c_int]),
+    "octree_cuc_set_stream": (None, [C.POINTER(octree_glc_t), C.c_uint64]),
+    "octree_cuc_reserve_frame": (None, [C.POINTER(octree_glc_t), C.c_int, C.c_int, C.c_int]),
+    "octree_cuc_ipc_export_frame": (None, [C.POINTER(octree_glc_t), C.c_void_p]),
+    "octree_cuc_ipc_open": (C.c_uint64, [C.POINTER(octree_glc_t), C.c_void_p]),
+    "octree_cuc_ipc_close": (None, [C.POINTER(octree_glc_t), C.c_uint64]),
     "octree_cuc_export_pending": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_void_p, C.c_size_t]),
     "octree_cuc_apply_blob": (None, [C.POINTER(octree_glc_t), C.c_void_p, C.c_size_t]),
     "octree_cuc_version": (C.c_char_p, []),
@@ -233,6 +238,25 @@ class OctreeGlc:
                                          pos.ctypes.data_as(C.c_void_p), ang.ctypes.data_as(C.c_void_p),
                                          float(lighta), int(quality), int(maxlevel), float(basesize), int(shoot))
         return pos.shape[0]
+
+    def set_stream(self, cuda_stream):
+        self.lib.octree_cuc_set_stream(self._p, int(cuda_stream))
+
+    def reserve_frame(self, width, height, views=1):
+        self.lib.octree_cuc_reserve_frame(self._p, int(width), int(height), int(views))
+
+    def ipc_export_frame(self):
+        h = np.zeros(64, dtype=np.uint8)
+        self.lib.octree_cuc_ipc_export_frame(self._p, h.ctypes.data_as(C.c_void_p))
+        return h
+
+    def ipc_open(self, handle):
+        h = np.ascontiguousarray(handle, dtype=np.uint8)
+        assert h.size == 64
+        return int(self.lib.octree_cuc_ipc_open(self._p, h.ctypes.data_as(C.c_void_p)))
+
+    def ipc_close(self, ptr):
+        self.lib.octree_cuc_ipc_close(self._p, int(ptr))
 
     def export_pending(self):
         need = self.lib.octree_cuc_export_pending(self._p, None, 0)

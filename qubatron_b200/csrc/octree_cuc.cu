@@ -168,7 +168,8 @@ constexpr int    VIEW_RING     = 4;
 struct Impl
 {
     int          device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;     // where all work is queued
+    cudaStream_t own_stream = nullptr; // created at init; `stream` unless the caller set one
     cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
     bool         timed = false;
 
@@ -757,7 +758,8 @@ octree_glc_t octree_glc_init(char* path)
     else
         CUDA_OK(cudaGetDevice(&I->device));
     CUDA_OK(cudaSetDevice(I->device));
-    CUDA_OK(cudaStreamCreateWithFlags(&I->stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaStreamCreateWithFlags(&I->own_stream, cudaStreamNonBlocking));
+    I->stream = I->own_stream;
     CUDA_OK(cudaEventCreate(&I->ev0));
     CUDA_OK(cudaEventCreate(&I->ev1));
     for (int i = 0; i < VIEW_RING; i++) CUDA_OK(cudaEventCreateWithFlags(&I->slot_ev[i], cudaEventDisableTiming));
@@ -806,7 +808,7 @@ void octree_cuc_destroy(octree_glc_t* rc)
     for (int i = 0; i < VIEW_RING; i++) cudaEventDestroy(I->slot_ev[i]);
     cudaEventDestroy(I->ev0);
     cudaEventDestroy(I->ev1);
-    cudaStreamDestroy(I->stream);
+    cudaStreamDestroy(I->own_stream);
     delete I;
     rc->impl          = nullptr;
     rc->memsize       = 0;
@@ -970,6 +972,61 @@ float octree_cuc_last_frame_ms(octree_glc_t* rc)
 }
 
 uint64_t octree_cuc_launch_count(octree_glc_t* rc) { return impl_of(rc)->launches; }
+
+void octree_cuc_set_stream(octree_glc_t* rc, uint64_t cuda_stream)
+{
+    Impl* I = impl_of(rc);
+    flush_pending(I);
+    CUDA_OK(cudaStreamSynchronize(I->stream));
+    I->stream = cuda_stream ? (cudaStream_t) (uintptr_t) cuda_stream : I->own_stream;
+}
+
+void octree_cuc_reserve_frame(octree_glc_t* rc, int width, int height, int views)
+{
+    Impl*  I      = impl_of(rc);
+    size_t pixels = (size_t) width * height * (views > 0 ? views : 1);
+    if (pixels <= I->frame_cap) return;
+    CUDA_OK(cudaStreamSynchronize(I->stream));
+    if (I->frame)
+    {
+        CUDA_OK(cudaFree(I->frame));
+        I->memsize -= I->frame_cap * 4;
+    }
+    CUDA_OK(cudaMalloc(&I->frame, pixels * 4));
+    CUDA_OK(cudaMemsetAsync(I->frame, 0, pixels * 4, I->stream));
+    CUDA_OK(cudaStreamSynchronize(I->stream));
+    I->frame_cap = pixels;
+    I->memsize += pixels * 4;
+    publish_memsize(rc, I);
+}
+
+void octree_cuc_ipc_export_frame(octree_glc_t* rc, uint8_t* handle64)
+{
+    Impl* I = impl_of(rc);
+    if (!I->frame) die("ipc_export_frame: reserve or render a frame first");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle is 64 bytes");
+    cudaIpcMemHandle_t h;
+    CUDA_OK(cudaIpcGetMemHandle(&h, I->frame));
+    memcpy(handle64, &h, 64);
+}
+
+uint64_t octree_cuc_ipc_open(octree_glc_t* rc, const uint8_t* handle64)
+{
+    impl_of(rc);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* p = nullptr;
+    CUDA_OK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    return (uint64_t) (uintptr_t) p;
+}
+
+void octree_cuc_ipc_close(octree_glc_t* rc, uint64_t device_ptr)
+{
+    Impl* I = impl_of(rc);
+    CUDA_OK(cudaStreamSynchronize(I->stream));
+    if (I->ext_target == device_ptr) I->ext_target = 0;
+    CUDA_OK(cudaIpcCloseMemHandle((void*) (uintptr_t) device_ptr));
+}
 
 // blob = { uint64 ndesc, uint64 payload_bytes, RangeDesc[ndesc], payload }
 size_t octree_cuc_export_pending(octree_glc_t* rc, void* blob_host, size_t capacity)

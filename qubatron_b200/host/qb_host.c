@@ -13,7 +13,7 @@
  *                                          L291-327 (grid index, x-major sort,
  *                                          first-point-per-cell compaction)
  * and tests/test_host_model.py checks node-for-node / point-for-point equality
- * with the reference's compiled code (oracle/_ref).
+ * with the reference's compiled code.
  *
  * Plain C ABI, used through ctypes by qubatron_b200/scene.py and from C by
  * examples/host_demo.c.

@@ -138,6 +138,7 @@ class Scene:
     levels: int = LEVELS
     raw_static: int = 0
     raw_dynamic: int = 0
+    cameras: list = None  # [(position, angle), ...] poses the configs are measured from
 
     def describe(self):
         return {"name": self.name, "static_points_raw": int(self.raw_static), "static_points": int(len(self.pnt_s)),
@@ -348,8 +349,9 @@ def make_c2(scale=1.0, spacing=0.30, seed=1234, zombie=True, progress=None):
             progress("terrain strip %d/%d" % (i // strip + 1, (len(xs) + strip - 1) // strip))
     # building shells on a jittered grid, skipping the camera / figure corridor
     rng = np.random.default_rng(seed)
-    pitch = 190.0
+    pitch = 174.0
     k = 0
+    inside = (0.0, 0.0, 0.0)
     for gx in np.arange(x_lo + 40.0, x_hi - 130.0, pitch):
         for gz in np.arange(z_lo + 40.0, z_hi - 130.0, pitch):
             bx = float(gx + rng.uniform(0, 30))
@@ -362,6 +364,8 @@ def make_c2(scale=1.0, spacing=0.30, seed=1234, zombie=True, progress=None):
             p, n = _box((bx, y0, bz), (bx + w, y0 + h, bz + d), spacing)
             tint = (int(rng.integers(110, 220)), int(rng.integers(100, 200)), int(rng.integers(90, 190)))
             parts.append((p, _colour(p, tint, seed + 100 + k), n))
+            if k == 0 or (abs(bx - 1000.0) + abs(bz - 600.0) < abs(inside[0] - 1000.0) + abs(inside[2] - 600.0)):
+                inside = (bx + 0.5 * w, y0 + 0.45 * h, bz + 0.5 * d)
             k += 1
     if progress:
         progress("%d buildings" % k)
@@ -375,10 +379,18 @@ def make_c2(scale=1.0, spacing=0.30, seed=1234, zombie=True, progress=None):
     dyn = None
     if zombie:
         by = float(_terrain_height(np.float32(760.0), np.float32(230.0)))
-        shells = 16 if scale >= 1.0 else max(2, int(16 * scale) + 1)
+        shells = 18 if scale >= 1.0 else max(2, int(18 * scale) + 1)
         dyn = zombie_raw(base=(760.0, by, 230.0), spacing=0.2, shells=shells)
     name = "c2_abandoned_%dM" % round(len(static_raw[0]) / 1e6)
-    return build_scene(name, static_raw, dyn)
+    sc = build_scene(name, static_raw, dyn)
+    gy = float(_terrain_height(np.float32(1100.0), np.float32(700.0)))
+    sc.cameras = [
+        CAMERA_C1,                                               # reference start pose, figure in view
+        ((inside[0], inside[1], inside[2]), (-2.438, -0.115, 0.0)),  # inside a building shell
+        ((880.0, 260.0, 640.0), (2.6, 0.55, 0.0)),               # looking up: mostly open sky
+        ((1100.0, gy + 2.5, 700.0), (-1.0, 0.0, 0.0)),           # grazing the terrain
+    ]
+    return sc
 
 
 def make_test5():

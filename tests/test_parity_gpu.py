@@ -1,0 +1,307 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the same inputs.
+
+Bar: flags (discard / leaf / shaded / shadow-visibility / disc) and all six hit-index planes bit-exact;
+RGBA within +-1/255 (parity.RGB_TOL).  Every test runs BOTH kernels (generic stack, fast register/shared
+stack) unless the base cube is not exactly representable, where only the generic kernel is legal."""
+import numpy as np
+import pytest
+
+import parity
+from oracle import qb_oracle as O
+from qubatron_b200 import connector as K
+from qubatron_b200 import scene as S
+
+pytestmark = pytest.mark.gpu
+
+KERNELS = [(K.KERNEL_GENERIC, "generic"), (K.KERNEL_FAST, "fast")]
+
+
+def _render_and_compare(sc, W, H, pos, ang, kernels=KERNELS, rc=None, **kw):
+    own = rc is None
+    if own:
+        rc = K.OctreeGlc(b"", device=0)
+        rc.upload_scene(sc)
+    rc.enable_aux(True)
+    rc.enable_counters(True)
+    ref = O.render(O.OracleScene(sc), O.uniforms(W, H, pos, ang, **kw))
+    outs = {}
+    for kern, name in kernels:
+        rc.set_kernel(kern)
+        rc.update(W, H, pos, ang, **kw)
+        rgba = rc.read_frame()
+        flags, aux = rc.read_aux()
+        outs[name] = parity.compare(rgba, flags, aux, ref, what=name)
+        assert rc.read_counters() == ref["counters"], name
+        assert rc.last_kernel() == kern
+    if own:
+        rc.destroy()
+    return ref, outs
+
+
+def test_c1_reference_start_pose(scene_c1):
+    """BASELINE config 1: 1 M-point cloud, 640x360, camera (700,150,350) angle (0.4636,0), light angle 0."""
+    ref, _ = _render_and_compare(scene_c1, 640, 360, *S.CAMERA_C1)
+    f = ref["flags"]
+    assert ((f & O.FLAG_SHADED) > 0).sum() > 100000 and ((f & O.FLAG_LIT) == 0).sum() > 1000
+
+
+@pytest.mark.parametrize("pos,ang,kw", [
+    ((700.0, 150.0, 350.0), (0.4636, 0.0, 0.0), dict(shoot=1, lighta=1.0)),
+    ((760.0, 125.0, 225.0), (2.0, 0.3, 0.0), {}),                 # camera inside the sphere
+    ((1200.0, 300.0, 900.0), (-0.9, -0.2, 0.0), {}),              # light disc visible
+    ((2600.0, 2300.0, 900.0), (-1.3, -0.5, 0.0), {}),             # outside the cube: discards
+    ((700.0, 100.3, 350.0), (0.4636, 0.02, 0.0), dict(lighta=4.0)),  # grazing the floor
+    ((760.0, 160.0, 330.0), (-0.7, -0.35, 0.0), dict(quality=8)),  # render size width/2
+])
+def test_c1_cameras(scene_c1, pos, ang, kw):
+    _render_and_compare(scene_c1, 640, 360, pos, ang, **kw)
+
+
+def test_axis_parallel_rays(scene_c1):
+    """angle (0,0): the centre columns have direction components that are exactly 0 or tiny
+    (octree_fsh.c L65/L78/L91 parallel-plane sentinel)."""
+    _render_and_compare(scene_c1, 320, 180, (750.0, 140.0, 330.0), (0.0, 0.0, 0.0))
+    _render_and_compare(scene_c1, 321, 181, (750.5, 140.25, 330.0), (np.pi / 2, 0.0, 0.0))
+
+
+def test_dynamic_tree_and_sparse_cloud(scene_random):
+    """Both trees populated and overlapping: dual-tree candidate merge (L313-317), dynamic override (L233-241),
+    heavy backtracking (80 expansions per ray)."""
+    ref, _ = _render_and_compare(scene_random, 256, 128, (760.0, 200.0, 420.0), (-0.05, -0.12, 0.0))
+    assert (ref["aux"][..., K.AUX_MODEL_D] > 0).sum() > 100
+
+
+def test_octtest_fixture():
+    """The reference's 5-point scene (modelutil.c L89-110) from (900,900,3000) (qubatron.c L136)."""
+    _render_and_compare(S.make_test5(), 320, 200, (900.0, 900.0, 3000.0), (0.0, 0.0, 0.0))
+
+
+def test_empty_scene():
+    """Nothing uploaded at all: every trace misses, frame is clear colour, no crash."""
+    rc = K.OctreeGlc(b"", device=0)
+    for kern, _ in KERNELS:
+        rc.set_kernel(kern)
+        rc.update(160, 90, (700.0, 150.0, 350.0), (0.3, 0.0, 0.0))
+        assert (rc.read_frame() == 0).all()
+    rc.destroy()
+
+
+def test_ragged_frame_sizes(scene_random):
+    """Frame sizes that are not multiples of the 16x8 CTA block or the 64x64 shard tile."""
+    for W, H in ((1, 1), (17, 9), (63, 65), (130, 70)):
+        _render_and_compare(scene_random, W, H, (760.0, 200.0, 420.0), (-0.05, -0.12, 0.0))
+
+
+@pytest.mark.parametrize("levels", [4, 9, 12])
+def test_other_depths(levels):
+    """maxlevel / -l option (qubatron.c L598-614): shallower trees on the same cube."""
+    sc = S.make_random(20000, 3000, seed=5, levels=levels)
+    _render_and_compare(sc, 200, 120, (760.0, 200.0, 420.0), (-0.05, -0.12, 0.0), maxlevel=levels)
+
+
+def test_inexact_base_cube_uses_generic_kernel():
+    """A base size whose grid is not exactly representable in fp32 must take the generic kernel and still match."""
+    sc = S.make_random(20000, 2000, seed=6, basesize=1000.1)
+    rc = K.OctreeGlc(b"", device=0)
+    rc.upload_scene(sc)
+    rc.enable_aux(True)
+    pos, ang = (422.0, 111.0, 233.0), (-0.05, -0.12, 0.0)
+    ref = O.render(O.OracleScene(sc), O.uniforms(200, 120, pos, ang, basesize=1000.1))
+    rc.set_kernel(K.KERNEL_AUTO)
+    rc.update(200, 120, pos, ang, basesize=1000.1)
+    assert rc.last_kernel() == K.KERNEL_GENERIC
+    flags, aux = rc.read_aux()
+    parity.compare(rc.read_frame(), flags, aux, ref, what="inexact")
+    assert ((ref["flags"] & O.FLAG_LEAF) > 0).sum() > 100
+    # and the auto choice for the reference cube is the fast kernel
+    rc.update(200, 120, pos, ang, basesize=1800.0)
+    assert rc.last_kernel() == K.KERNEL_FAST
+    rc.destroy()
+
+
+def test_range_updates_zero_and_append(scene_c1):
+    """modelutil_punch_hole's upload pattern (modelutil.c L429-437, L486-501, L528-546): zero child slots,
+    append paths, upload each touched 48-byte node, then a colour/normal sub-range.  The device copy must equal
+    a fresh full upload of the final host arrays, and both must match the oracle."""
+    tree = S.HostOctree()
+    tree.insert_points(scene_c1.pnt_s)
+    col = scene_c1.col_s.copy()
+    nrm = scene_c1.nrm_s.copy()
+    rc = K.OctreeGlc(b"", device=0)
+    rc.upload_points(col, K.STATIC_COLOR)
+    rc.upload_points(nrm, K.STATIC_NORMAL)
+    rc.upload_octree(tree.nodes(copy=False))
+    rc.upload_octree(np.zeros((1, 12), np.int32), dynamic=True)
+
+    rng = np.random.default_rng(3)
+    centre = np.array([760.0, 125.0, 245.0], np.float32)  # front of the sphere
+    cand = np.nonzero(np.linalg.norm(scene_c1.pnt_s - centre[None, :], axis=1) < 9.0)[0]
+    victims = rng.choice(cand, size=min(400, len(cand)), replace=False)
+    touched_models = []
+    for v in victims:
+        m, o = tree.remove_point(scene_c1.pnt_s[v])
+        if o >= 0:
+            nodes = tree.nodes(copy=False)
+            rc.upload_texbuffer_data(nodes, K.GL_INT, len(nodes) * 48, 16, o * 48, (o + 1) * 48, K.STATIC_OCTREE)
+            touched_models.append(m)
+    for m in touched_models:
+        newp = scene_c1.pnt_s[m] + rng.normal(0, 3.0, size=3).astype(np.float32)
+        t = tree.insert_point(newp, m)
+        nodes = tree.nodes(copy=False)
+        for j in t:
+            if j > 0:
+                rc.upload_texbuffer_data(nodes, K.GL_INT, len(nodes) * 48, 16, int(j) * 48, (int(j) + 1) * 48,
+                                         K.STATIC_OCTREE)
+        col[m] += 0.2
+        nrm[m] = centre - newp
+    lo, hi = min(touched_models), max(touched_models) + 1
+    rc.upload_points(col, K.STATIC_COLOR, lo, hi)
+    rc.upload_points(nrm, K.STATIC_NORMAL, lo, hi)
+
+    final = S.Scene("punched", scene_c1.pnt_s, col, nrm, tree.nodes(), scene_c1.pnt_d, scene_c1.col_d,
+                    scene_c1.nrm_d, scene_c1.oct_d)
+    pos, ang = (745.0, 135.0, 300.0), (0.15, -0.1, 0.0)
+    ref, _ = _render_and_compare(final, 320, 180, pos, ang, rc=rc, shoot=1)
+    rc.destroy()
+    # the hole changed the picture
+    before = O.render(O.OracleScene(scene_c1), O.uniforms(320, 180, pos, ang, shoot=1))
+    assert (before["aux"] != ref["aux"]).any()
+
+
+def test_texel_granularity_of_uploads(scene_random):
+    """start/end are rounded DOWN to itemsize (octree_glc.c L432-433): a range that covers part of an item
+    must not upload that item."""
+    sc = scene_random
+    rc = K.OctreeGlc(b"", device=0)
+    rc.upload_scene(sc)
+    wrong = sc.oct_s.copy()
+    wrong[100:200, :8] = 0
+    # bytes [100*48 + 5, 200*48 - 3) -> items [300, 599): node 199's last texel (model index + pad) is skipped,
+    # node 100's first texel IS included because start rounds down
+    rc.upload_texbuffer_data(wrong, K.GL_INT, wrong.size * 4, 16, 100 * 48 + 5, 200 * 48 - 3, K.STATIC_OCTREE)
+    expect = sc.oct_s.copy()
+    expect[100:200, :8] = 0
+    final = S.Scene("granular", sc.pnt_s, sc.col_s, sc.nrm_s, expect, sc.pnt_d, sc.col_d, sc.nrm_d, sc.oct_d)
+    _render_and_compare(final, 160, 90, (760.0, 200.0, 420.0), (-0.05, -0.12, 0.0), rc=rc)
+    rc.destroy()
+
+
+def test_growth_keeps_contents(scene_random):
+    """Appending beyond the device capacity (size grows) re-uploads the whole array like the reference
+    (octree_glc.c L412-428) and keeps rendering correct."""
+    sc = scene_random
+    rc = K.OctreeGlc(b"", device=0)
+    half = len(sc.oct_s) // 2
+    # first a truncated tree (children pointing past the uploaded range read as absent)
+    rc.upload_points(sc.col_s, K.STATIC_COLOR)
+    rc.upload_points(sc.nrm_s, K.STATIC_NORMAL)
+    rc.upload_texbuffer_data(sc.oct_s[:half].copy(), K.GL_INT, half * 48, 16, 0, half * 48, K.STATIC_OCTREE)
+    rc.update(64, 32, (760.0, 200.0, 420.0), (-0.05, -0.12, 0.0))
+    rc.sync()
+    # then the whole array with a range that only names the tail
+    rc.upload_texbuffer_data(sc.oct_s, K.GL_INT, len(sc.oct_s) * 48, 16, half * 48, len(sc.oct_s) * 48,
+                             K.STATIC_OCTREE)
+    rc.upload_points(sc.col_d, K.DYNAMIC_COLOR)
+    rc.upload_points(sc.nrm_d, K.DYNAMIC_NORMAL)
+    rc.upload_octree(sc.oct_d, dynamic=True)
+    _render_and_compare(sc, 160, 90, (760.0, 200.0, 420.0), (-0.05, -0.12, 0.0), rc=rc)
+    assert rc.memsize > 0
+    rc.destroy()
+
+
+def test_multi_view_batch(scene_random):
+    """octree_cuc_update_views: n views in one launch equal n single frames."""
+    rng = np.random.default_rng(777)
+    n = 5
+    pos = np.stack([rng.uniform(700, 900, n), rng.uniform(150, 260, n), rng.uniform(250, 500, n)], axis=1)
+    ang = np.stack([rng.uniform(-0.6, 0.6, n), rng.uniform(-0.4, 0.2, n), np.zeros(n)], axis=1)
+    rc = K.OctreeGlc(b"", device=0)
+    rc.upload_scene(scene_random)
+    rc.enable_aux(True)
+    osc = O.OracleScene(scene_random)
+    for kern, name in KERNELS:
+        rc.set_kernel(kern)
+        rc.update_views(128, 64, pos, ang)
+        rgba = rc.read_frame(views=n).reshape(n, 64, 128, 4)
+        flags, aux = rc.read_aux(views=n)
+        flags, aux = flags.reshape(n, 64, 128), aux.reshape(n, 64, 128, 6)
+        for v in range(n):
+            ref = O.render(osc, O.uniforms(128, 64, pos[v], ang[v]))
+            parity.compare(rgba[v], flags[v], aux[v], ref, what="%s view %d" % (name, v))
+    rc.destroy()
+
+
+def test_tile_sharding_on_one_gpu(scene_random):
+    """Image-tile sharding: world ranks render disjoint interleaved tiles; their union is the full frame."""
+    W, H, world = 200, 150, 3
+    pos, ang = (760.0, 200.0, 420.0), (-0.05, -0.12, 0.0)
+    ref = O.render(O.OracleScene(scene_random), O.uniforms(W, H, pos, ang))
+    rc = K.OctreeGlc(b"", device=0)
+    rc.upload_scene(scene_random)
+    for kern, name in KERNELS:
+        rc.set_kernel(kern)
+        acc = np.zeros((H, W, 4), np.uint8)
+        owner = np.full((H, W), -1)
+        for r in range(world):
+            rc.set_shard(r, world, 32, 16)
+            # poison, then render: only this rank's tiles may change
+            rc.set_shard(0, 1, 32, 16)
+            rc.update(W, H, (5000.0, 5000.0, 5000.0), (0.0, 0.0, 0.0))  # all-discard frame = zeros
+            rc.set_shard(r, world, 32, 16)
+            rc.update(W, H, pos, ang)
+            f = rc.read_frame()
+            ty, tx = np.arange(H)[:, None] // 16, np.arange(W)[None, :] // 32
+            mine = ((ty * ((W + 31) // 32) + tx) % world) == r
+            assert (f[~mine] == 0).all(), name
+            acc[mine] = f[mine]
+            owner[mine] = r
+        assert (owner >= 0).all()
+        assert np.abs(acc.astype(np.int16) - ref["rgba"].astype(np.int16)).max() <= parity.RGB_TOL, name
+    rc.destroy()
+
+
+def test_external_frame_target(scene_random):
+    """Rendering straight into caller-owned device memory (a torch tensor) with a row pitch."""
+    import torch
+    W, H, pitch = 120, 50, 128
+    pos, ang = (760.0, 200.0, 420.0), (-0.05, -0.12, 0.0)
+    ref = O.render(O.OracleScene(scene_random), O.uniforms(W, H, pos, ang))
+    buf = torch.zeros((H, pitch, 4), dtype=torch.uint8, device="cuda:0")
+    rc = K.OctreeGlc(b"", device=0)
+    rc.upload_scene(scene_random)
+    rc.set_frame_target(buf.data_ptr(), pitch, keepalive=buf)
+    rc.update(W, H, pos, ang)
+    rc.sync()
+    got = buf.cpu().numpy()
+    assert np.abs(got[:, :W].astype(np.int16) - ref["rgba"].astype(np.int16)).max() <= parity.RGB_TOL
+    assert (got[:, W:] == 0).all()
+    rc.destroy()
+
+
+def test_full_size_properties(scene_c1):
+    """1920x1080 (BASELINE full frame size) through size-independent properties: both kernels agree bit for
+    bit with each other, counters agree, alpha is 255 exactly on leaf pixels, shadowed pixels are darker than
+    their lit version would be (LIT bit off => no 0.7 light term)."""
+    rc = K.OctreeGlc(b"", device=0)
+    rc.upload_scene(scene_c1)
+    rc.enable_aux(True)
+    rc.enable_counters(True)
+    out = {}
+    for kern, name in KERNELS:
+        rc.set_kernel(kern)
+        rc.update(1920, 1080, *S.CAMERA_C1)
+        out[name] = (rc.read_frame(), rc.read_aux(), rc.read_counters())
+    g, f = out["generic"], out["fast"]
+    assert np.array_equal(g[0], f[0]) and np.array_equal(g[1][0], f[1][0]) and np.array_equal(g[1][1], f[1][1])
+    assert g[2] == f[2]
+    flags = f[1][0]
+    leaf = (flags & K.FLAG_LEAF) > 0
+    assert ((f[0][..., 3] == 255) == leaf).all()
+    assert f[2]["rays_primary"] == 1920 * 1080 and f[2]["rays_shadow"] == int(((flags & K.FLAG_SHADED) > 0).sum())
+    # a sub-window rendered by the oracle pins the full-size frame to the reference semantics
+    u = O.uniforms(1920, 1080, *S.CAMERA_C1)
+    ref = O.render(O.OracleScene(scene_c1), u, rows=(500, 560))
+    assert np.array_equal(ref["flags"][500:560], flags[500:560])
+    assert np.array_equal(ref["aux"][500:560], f[1][1][500:560])
+    assert np.abs(ref["rgba"][500:560].astype(np.int16) - f[0][500:560].astype(np.int16)).max() <= parity.RGB_TOL
+    rc.destroy()
