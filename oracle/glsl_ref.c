@@ -1,0 +1,413 @@
+/*
+ * glsl_ref.c -- runs the reference's UNMODIFIED shaders (octree_vsh.c / octree_fsh.c)
+ * headless on Mesa llvmpipe and dumps the frame.
+ *
+ * TEST INFRASTRUCTURE ONLY.  The shader sources are NOT in this repository: the
+ * Makefile embeds them as binary blobs from /root/reference/src/qubatron/shaders/
+ * into oracle/_ref/ (git-ignored).  This harness restates only the host side of
+ *   /root/reference/src/qubatron/octree_glc.c L93-247 (program, 6 data textures
+ *   8192 texels wide, render target), L263-305 (uniforms, quad), L361-498
+ *   (texture addressing: linear index -> (i mod 8192, i / 8192))
+ * because octree_glc.c itself needs SDL2/GLEW, which this image does not have.
+ *
+ * GL comes from the Mesa 18.1.9 libGL.so.1 (llvmpipe, GLX/xlib flavour) bundled
+ * with Nsight Compute, dlopen'ed after oracle/_ref/libX11.so.6 / libXext.so.6
+ * (x11_stub.c) so that no X server is needed.
+ *
+ * usage: glsl_ref <in.bin> <out.rgba> [mode] [repeat]
+ *   in.bin : int64 hdr[8] = {nodes_s, nodes_d, points_s, points_d, W, H, maxlevel, shoot}
+ *            float  u[14]  = {camfp3, angle3, light3, basecube4... see below}
+ *            then oct_s, oct_d (int32 x12 per node), col_s, nrm_s, col_d, nrm_d (float x3)
+ *   mode 0 : the shader exactly as shipped -> RGBA8 frame
+ *   mode 1 : aux dump of the static model index  (output statement patched only)
+ *   mode 2 : aux dump of the dynamic model index
+ *   mode 3 : aux dump of the shadow visibility step(sqr, 15.0)
+ *   The aux modes append statements that copy a value to the output; the traversal
+ *   and shading code is untouched.
+ * prints one JSON line with renderer, version and per-frame seconds.
+ */
+#define _GNU_SOURCE
+#include <dlfcn.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+extern const char _binary_octree_fsh_c_start[], _binary_octree_fsh_c_end[];
+extern const char _binary_octree_vsh_c_start[], _binary_octree_vsh_c_end[];
+
+#ifndef MESA_DIR
+    #define MESA_DIR "/opt/nvidia/nsight-compute/2025.2.1/host/linux-desktop-glibc_2_11_3-x64/Mesa"
+#endif
+
+typedef unsigned int GLenum, GLuint, GLbitfield;
+typedef int          GLint, GLsizei;
+typedef float        GLfloat;
+typedef char         GLchar;
+typedef long         GLsizeiptr;
+
+#define GL_FRAGMENT_SHADER 0x8B30
+#define GL_VERTEX_SHADER 0x8B31
+#define GL_COMPILE_STATUS 0x8B81
+#define GL_LINK_STATUS 0x8B82
+#define GL_TEXTURE_2D 0x0DE1
+#define GL_TEXTURE_MAG_FILTER 0x2800
+#define GL_TEXTURE_MIN_FILTER 0x2801
+#define GL_NEAREST 0x2600
+#define GL_LINEAR 0x2601
+#define GL_RGB32F 0x8815
+#define GL_RGBA32I 0x8D82
+#define GL_RGB 0x1907
+#define GL_RGBA 0x1908
+#define GL_RGBA_INTEGER 0x8D99
+#define GL_FLOAT 0x1406
+#define GL_INT 0x1404
+#define GL_UNSIGNED_BYTE 0x1401
+#define GL_TEXTURE0 0x84C0
+#define GL_FRAMEBUFFER 0x8D40
+#define GL_COLOR_ATTACHMENT0 0x8CE0
+#define GL_FRAMEBUFFER_COMPLETE 0x8CD5
+#define GL_COLOR_BUFFER_BIT 0x4000
+#define GL_DEPTH_BUFFER_BIT 0x0100
+#define GL_ARRAY_BUFFER 0x8892
+#define GL_DYNAMIC_DRAW 0x88E8
+#define GL_TRIANGLES 4
+#define GL_BLEND 0x0BE2
+#define GL_RENDERER 0x1F01
+#define GL_VERSION 0x1F02
+#define GL_PACK_ALIGNMENT 0x0D05
+#define GL_UNPACK_ALIGNMENT 0x0CF5
+
+#define GLX_RGBA 4
+#define GLX_DOUBLEBUFFER 5
+#define GLX_RED_SIZE 8
+#define GLX_GREEN_SIZE 9
+#define GLX_BLUE_SIZE 10
+#define GLX_DEPTH_SIZE 12
+
+static void* (*p_glXGetProcAddress)(const char*);
+#define GLFN(ret, name, ...)                                                                                          \
+    static ret (*name)(__VA_ARGS__);
+GLFN(GLuint, glCreateShader, GLenum)
+GLFN(void, glShaderSource, GLuint, GLsizei, const GLchar**, const GLint*)
+GLFN(void, glCompileShader, GLuint)
+GLFN(void, glGetShaderiv, GLuint, GLenum, GLint*)
+GLFN(void, glGetShaderInfoLog, GLuint, GLsizei, GLsizei*, GLchar*)
+GLFN(GLuint, glCreateProgram, void)
+GLFN(void, glAttachShader, GLuint, GLuint)
+GLFN(void, glBindAttribLocation, GLuint, GLuint, const GLchar*)
+GLFN(void, glLinkProgram, GLuint)
+GLFN(void, glGetProgramiv, GLuint, GLenum, GLint*)
+GLFN(void, glGetProgramInfoLog, GLuint, GLsizei, GLsizei*, GLchar*)
+GLFN(void, glUseProgram, GLuint)
+GLFN(GLint, glGetUniformLocation, GLuint, const GLchar*)
+GLFN(void, glUniform1i, GLint, GLint)
+GLFN(void, glUniform2fv, GLint, GLsizei, const GLfloat*)
+GLFN(void, glUniform3fv, GLint, GLsizei, const GLfloat*)
+GLFN(void, glUniform4fv, GLint, GLsizei, const GLfloat*)
+GLFN(void, glUniformMatrix4fv, GLint, GLsizei, unsigned char, const GLfloat*)
+GLFN(void, glGenTextures, GLsizei, GLuint*)
+GLFN(void, glBindTexture, GLenum, GLuint)
+GLFN(void, glTexParameteri, GLenum, GLenum, GLint)
+GLFN(void, glTexImage2D, GLenum, GLint, GLint, GLsizei, GLsizei, GLint, GLenum, GLenum, const void*)
+GLFN(void, glActiveTexture, GLenum)
+GLFN(void, glGenFramebuffers, GLsizei, GLuint*)
+GLFN(void, glBindFramebuffer, GLenum, GLuint)
+GLFN(void, glFramebufferTexture2D, GLenum, GLenum, GLenum, GLuint, GLint)
+GLFN(GLenum, glCheckFramebufferStatus, GLenum)
+GLFN(void, glViewport, GLint, GLint, GLsizei, GLsizei)
+GLFN(void, glClearColor, GLfloat, GLfloat, GLfloat, GLfloat)
+GLFN(void, glClear, GLbitfield)
+GLFN(void, glGenBuffers, GLsizei, GLuint*)
+GLFN(void, glBindBuffer, GLenum, GLuint)
+GLFN(void, glBufferData, GLenum, GLsizeiptr, const void*, GLenum)
+GLFN(void, glGenVertexArrays, GLsizei, GLuint*)
+GLFN(void, glBindVertexArray, GLuint)
+GLFN(void, glEnableVertexAttribArray, GLuint)
+GLFN(void, glVertexAttribPointer, GLuint, GLint, GLenum, unsigned char, GLsizei, const void*)
+GLFN(void, glDrawArrays, GLenum, GLint, GLsizei)
+GLFN(void, glFinish, void)
+GLFN(void, glReadPixels, GLint, GLint, GLsizei, GLsizei, GLenum, GLenum, void*)
+GLFN(const unsigned char*, glGetString, GLenum)
+GLFN(GLenum, glGetError, void)
+GLFN(void, glEnable, GLenum)
+GLFN(void, glPixelStorei, GLenum, GLint)
+
+static void die(const char* m)
+{
+    fprintf(stderr, "glsl_ref: %s\n", m);
+    exit(2);
+}
+
+static void* need(void* h, const char* n)
+{
+    void* p = h ? dlsym(h, n) : p_glXGetProcAddress(n);
+    if (!p)
+    {
+        fprintf(stderr, "glsl_ref: missing symbol %s\n", n);
+        exit(2);
+    }
+    return p;
+}
+
+static double now(void)
+{
+    struct timespec t;
+    clock_gettime(CLOCK_MONOTONIC, &t);
+    return t.tv_sec + 1e-9 * t.tv_nsec;
+}
+
+/* replace the first occurrence of `needle`; the shader text is only ever EXTENDED around output statements */
+static char* patch(char* src, const char* needle, const char* repl)
+{
+    char* at = strstr(src, needle);
+    if (!at) die("aux patch point not found in the reference shader");
+    size_t a = (size_t) (at - src), nl = strlen(needle), rl = strlen(repl), sl = strlen(src);
+    char*  out = malloc(sl - nl + rl + 1);
+    memcpy(out, src, a);
+    memcpy(out + a, repl, rl);
+    memcpy(out + a + rl, at + nl, sl - a - nl + 1);
+    free(src);
+    return out;
+}
+
+static GLuint compile(GLenum type, const char* src)
+{
+    GLuint s = glCreateShader(type);
+    glShaderSource(s, 1, &src, NULL);
+    glCompileShader(s);
+    GLint ok = 0;
+    glGetShaderiv(s, GL_COMPILE_STATUS, &ok);
+    if (!ok)
+    {
+        char log[4096];
+        glGetShaderInfoLog(s, sizeof(log), NULL, log);
+        fprintf(stderr, "glsl_ref: shader compile failed:\n%s\n", log);
+        exit(2);
+    }
+    return s;
+}
+
+/* 8192-texel-wide data texture, rows = ceil(texels / 8192) (octree_glc.c L412-428) */
+static GLuint data_texture(int unit, const void* data, size_t texels, int is_int)
+{
+    size_t rows = (texels + 8191) / 8192;
+    if (rows == 0) rows = 1;
+    if (rows > 8192) die("scene exceeds the reference's 8192x8192 texture cap");
+    size_t texel_bytes = is_int ? 16 : 12;
+    char*  padded      = calloc(rows * 8192, texel_bytes);
+    if (texels) memcpy(padded, data, texels * texel_bytes);
+    GLuint t;
+    glGenTextures(1, &t);
+    glActiveTexture(GL_TEXTURE0 + unit);
+    glBindTexture(GL_TEXTURE_2D, t);
+    glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_MAG_FILTER, GL_NEAREST);
+    glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_MIN_FILTER, GL_NEAREST);
+    if (is_int)
+        glTexImage2D(GL_TEXTURE_2D, 0, GL_RGBA32I, 8192, (GLsizei) rows, 0, GL_RGBA_INTEGER, GL_INT, padded);
+    else
+        glTexImage2D(GL_TEXTURE_2D, 0, GL_RGB32F, 8192, (GLsizei) rows, 0, GL_RGB, GL_FLOAT, padded);
+    free(padded);
+    return t;
+}
+
+int main(int argc, char** argv)
+{
+    if (argc < 3) die("usage: glsl_ref in.bin out.rgba [mode] [repeat]");
+    int mode   = argc > 3 ? atoi(argv[3]) : 0;
+    int repeat = argc > 4 ? atoi(argv[4]) : 1;
+
+    /* ---- input ---- */
+    FILE* f = fopen(argv[1], "rb");
+    if (!f) die("cannot open input");
+    int64_t hdr[8];
+    float   u[16];
+    if (fread(hdr, 8, 8, f) != 8 || fread(u, 4, 16, f) != 16) die("short input header");
+    int64_t nodes_s = hdr[0], nodes_d = hdr[1], pts_s = hdr[2], pts_d = hdr[3];
+    int     W = (int) hdr[4], H = (int) hdr[5], maxlevel = (int) hdr[6], shoot = (int) hdr[7];
+    /* u: camfp[0..2] angle[3..5] light[6..8] basecube[9..12] dims[13..14] */
+    int32_t* oct_s = malloc((size_t) (nodes_s ? nodes_s : 1) * 48);
+    int32_t* oct_d = malloc((size_t) (nodes_d ? nodes_d : 1) * 48);
+    float*   col_s = malloc((size_t) (pts_s ? pts_s : 1) * 12);
+    float*   nrm_s = malloc((size_t) (pts_s ? pts_s : 1) * 12);
+    float*   col_d = malloc((size_t) (pts_d ? pts_d : 1) * 12);
+    float*   nrm_d = malloc((size_t) (pts_d ? pts_d : 1) * 12);
+    if (fread(oct_s, 48, nodes_s, f) != (size_t) nodes_s || fread(oct_d, 48, nodes_d, f) != (size_t) nodes_d ||
+        fread(col_s, 12, pts_s, f) != (size_t) pts_s || fread(nrm_s, 12, pts_s, f) != (size_t) pts_s ||
+        fread(col_d, 12, pts_d, f) != (size_t) pts_d || fread(nrm_d, 12, pts_d, f) != (size_t) pts_d)
+        die("short input body");
+    fclose(f);
+    if (W > 2048 || H > 2048) die("the reference's render target is 2048x2048 (octree_glc.c L237)");
+
+    /* ---- GL via the stubbed X11 + Mesa llvmpipe ---- */
+    char  path[4096];
+    char* self = realpath("/proc/self/exe", NULL);
+    char* dir  = self ? self : strdup("./x");
+    *strrchr(dir, '/') = 0;
+    snprintf(path, sizeof(path), "%s/libX11.so.6", dir);
+    void* x11 = dlopen(path, RTLD_NOW | RTLD_GLOBAL);
+    if (!x11) die(dlerror());
+    snprintf(path, sizeof(path), "%s/libXext.so.6", dir);
+    if (!dlopen(path, RTLD_NOW | RTLD_GLOBAL)) die(dlerror());
+    const char* mesa = getenv("QB_MESA_LIBGL") ? getenv("QB_MESA_LIBGL") : MESA_DIR "/libGL.so.1";
+    void*       gl   = dlopen(mesa, RTLD_NOW | RTLD_GLOBAL);
+    if (!gl) die(dlerror());
+
+    void* (*open_display)(int, int) = need(x11, "qb_stub_open_display");
+    void* dpy                       = open_display(64, 64);
+
+    void* (*glXChooseVisual)(void*, int, int*)        = need(gl, "glXChooseVisual");
+    void* (*glXCreateContext)(void*, void*, void*, int) = need(gl, "glXCreateContext");
+    int (*glXMakeCurrent)(void*, unsigned long, void*) = need(gl, "glXMakeCurrent");
+    p_glXGetProcAddress                                = need(gl, "glXGetProcAddressARB");
+
+    int   attribs[] = {GLX_RGBA, GLX_RED_SIZE, 8, GLX_GREEN_SIZE, 8, GLX_BLUE_SIZE, 8, GLX_DEPTH_SIZE, 24,
+                       GLX_DOUBLEBUFFER, 0};
+    void* vi        = glXChooseVisual(dpy, 0, attribs);
+    if (!vi) die("glXChooseVisual failed");
+    void* ctx = glXCreateContext(dpy, vi, NULL, 1);
+    if (!ctx) die("glXCreateContext failed");
+    if (!glXMakeCurrent(dpy, 1, ctx)) die("glXMakeCurrent failed");
+
+#define LOAD(n) n = need(NULL, #n);
+    LOAD(glCreateShader) LOAD(glShaderSource) LOAD(glCompileShader) LOAD(glGetShaderiv) LOAD(glGetShaderInfoLog)
+    LOAD(glCreateProgram) LOAD(glAttachShader) LOAD(glBindAttribLocation) LOAD(glLinkProgram) LOAD(glGetProgramiv)
+    LOAD(glGetProgramInfoLog) LOAD(glUseProgram) LOAD(glGetUniformLocation) LOAD(glUniform1i) LOAD(glUniform2fv)
+    LOAD(glUniform3fv) LOAD(glUniform4fv) LOAD(glUniformMatrix4fv) LOAD(glGenTextures) LOAD(glBindTexture)
+    LOAD(glTexParameteri) LOAD(glTexImage2D) LOAD(glActiveTexture) LOAD(glGenFramebuffers) LOAD(glBindFramebuffer)
+    LOAD(glFramebufferTexture2D) LOAD(glCheckFramebufferStatus) LOAD(glViewport) LOAD(glClearColor) LOAD(glClear)
+    LOAD(glGenBuffers) LOAD(glBindBuffer) LOAD(glBufferData) LOAD(glGenVertexArrays) LOAD(glBindVertexArray)
+    LOAD(glEnableVertexAttribArray) LOAD(glVertexAttribPointer) LOAD(glDrawArrays) LOAD(glFinish) LOAD(glReadPixels)
+    LOAD(glGetString) LOAD(glGetError) LOAD(glEnable) LOAD(glPixelStorei)
+
+    /* ---- shaders: the reference text, byte for byte (mode 0) ---- */
+    size_t fl  = (size_t) (_binary_octree_fsh_c_end - _binary_octree_fsh_c_start);
+    size_t vl  = (size_t) (_binary_octree_vsh_c_end - _binary_octree_vsh_c_start);
+    char*  fsh = malloc(fl + 1);
+    char*  vsh = malloc(vl + 1);
+    memcpy(fsh, _binary_octree_fsh_c_start, fl);
+    fsh[fl] = 0;
+    memcpy(vsh, _binary_octree_vsh_c_start, vl);
+    vsh[vl] = 0;
+    const char* pack = "{ int qv = floatBitsToInt(qb_out); fragColor = vec4(float(qv & 255) / 255.0, "
+                       "float((qv >> 8) & 255) / 255.0, float((qv >> 16) & 255) / 255.0, "
+                       "float((qv >> 24) & 255) / 255.0); }";
+    if (mode != 0)
+    {
+        fsh = patch(fsh, "out vec4 fragColor;", "out vec4 fragColor;\nfloat qb_out = intBitsToFloat(-1);");
+        fsh = patch(fsh, "fragColor = col;", pack);
+    }
+    if (mode == 1)
+        fsh = patch(fsh, "int docti = oct_from_octets_for_index(8, stck[level].docti, octtexbuf_d, level);",
+                    "int docti = oct_from_octets_for_index(8, stck[level].docti, octtexbuf_d, level);\n"
+                    "qb_out = intBitsToFloat(socti);");
+    if (mode == 2)
+        fsh = patch(fsh, "int docti = oct_from_octets_for_index(8, stck[level].docti, octtexbuf_d, level);",
+                    "int docti = oct_from_octets_for_index(8, stck[level].docti, octtexbuf_d, level);\n"
+                    "qb_out = intBitsToFloat(docti);");
+    if (mode == 3)
+        fsh = patch(fsh, "col.z *= 0.7;", "col.z *= 0.7;\nqb_out = intBitsToFloat(int(step(sqr, 15.0)));");
+
+    GLuint prog = glCreateProgram();
+    glAttachShader(prog, compile(GL_VERTEX_SHADER, vsh));
+    glAttachShader(prog, compile(GL_FRAGMENT_SHADER, fsh));
+    glBindAttribLocation(prog, 0, "position"); /* octree_glc.c L113 (before link here) */
+    glLinkProgram(prog);
+    GLint ok = 0;
+    glGetProgramiv(prog, GL_LINK_STATUS, &ok);
+    if (!ok)
+    {
+        char log[4096];
+        glGetProgramInfoLog(prog, sizeof(log), NULL, log);
+        fprintf(stderr, "glsl_ref: link failed:\n%s\n", log);
+        return 2;
+    }
+    glUseProgram(prog);
+
+    /* ---- data textures on units unif+1 as in octree_glc.c L371-408 ---- */
+    glPixelStorei(GL_UNPACK_ALIGNMENT, 1);
+    glPixelStorei(GL_PACK_ALIGNMENT, 1);
+    struct
+    {
+        const char* name;
+        int         unit;
+        const void* data;
+        size_t      texels;
+        int         is_int;
+    } tex[6] = {{"coltexbuf_s", 7, col_s, (size_t) pts_s, 0},       {"coltexbuf_d", 8, col_d, (size_t) pts_d, 0},
+                {"nrmtexbuf_s", 9, nrm_s, (size_t) pts_s, 0},       {"nrmtexbuf_d", 10, nrm_d, (size_t) pts_d, 0},
+                {"octtexbuf_s", 11, oct_s, (size_t) nodes_s * 3, 1}, {"octtexbuf_d", 12, oct_d, (size_t) nodes_d * 3, 1}};
+    for (int i = 0; i < 6; i++)
+    {
+        data_texture(tex[i].unit, tex[i].data, tex[i].texels, tex[i].is_int);
+        glUniform1i(glGetUniformLocation(prog, tex[i].name), tex[i].unit);
+    }
+
+    /* ---- 2048x2048 RGBA8 render target (octree_glc.c L230-244) ---- */
+    GLuint fbo, rt;
+    glGenFramebuffers(1, &fbo);
+    glBindFramebuffer(GL_FRAMEBUFFER, fbo);
+    glGenTextures(1, &rt);
+    glActiveTexture(GL_TEXTURE0);
+    glBindTexture(GL_TEXTURE_2D, rt);
+    glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_MAG_FILTER, GL_LINEAR);
+    glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_MIN_FILTER, GL_LINEAR);
+    glTexImage2D(GL_TEXTURE_2D, 0, GL_RGBA, 2048, 2048, 0, GL_RGBA, GL_UNSIGNED_BYTE, 0);
+    glBindTexture(GL_TEXTURE_2D, 0);
+    glFramebufferTexture2D(GL_FRAMEBUFFER, GL_COLOR_ATTACHMENT0, GL_TEXTURE_2D, rt, 0);
+    if (glCheckFramebufferStatus(GL_FRAMEBUFFER) != GL_FRAMEBUFFER_COMPLETE) die("framebuffer incomplete");
+
+    /* ---- uniforms (octree_glc.c L263-284); ortho = m4_defaultortho(0,ow,0,oh,-10,10), mt_matrix_4d.c L179-210 ---- */
+    float ow = u[13], oh = u[14];
+    float proj[16] = {0};
+    proj[0]        = 2.0f / (ow - 0.0f);
+    proj[5]        = 2.0f / (oh - 0.0f);
+    proj[10]       = -2.0f / (10.0f - -10.0f);
+    proj[12]       = -(ow + 0.0f) / (ow - 0.0f);
+    proj[13]       = -(oh + 0.0f) / (oh - 0.0f);
+    proj[14]       = -(10.0f + -10.0f) / (10.0f - -10.0f);
+    proj[15]       = 1.0f;
+    glEnable(GL_BLEND); /* L251 (blend func stays ONE/ZERO) */
+    glUniformMatrix4fv(glGetUniformLocation(prog, "projection"), 1, 0, proj);
+    glUniform3fv(glGetUniformLocation(prog, "camfp"), 1, u + 0);
+    glUniform3fv(glGetUniformLocation(prog, "angle_in"), 1, u + 3);
+    glUniform3fv(glGetUniformLocation(prog, "light"), 1, u + 6);
+    glUniform4fv(glGetUniformLocation(prog, "basecube"), 1, u + 9);
+    glUniform2fv(glGetUniformLocation(prog, "dimensions"), 1, u + 13);
+    glUniform1i(glGetUniformLocation(prog, "maxlevel"), maxlevel);
+    glUniform1i(glGetUniformLocation(prog, "shoot"), shoot);
+
+    GLuint vbo, vao;
+    glGenBuffers(1, &vbo);
+    glBindBuffer(GL_ARRAY_BUFFER, vbo);
+    glGenVertexArrays(1, &vao);
+    glBindVertexArray(vao);
+    glEnableVertexAttribArray(0);
+    glVertexAttribPointer(0, 3, GL_FLOAT, 0, sizeof(GLfloat) * 3, 0);
+    GLfloat quad[] = {0.0f, 0.0f, 0.0f, ow, 0.0f, 0.0f, 0.0f, oh, 0.0f, 0.0f, oh, 0.0f, ow, 0.0f, 0.0f, ow, oh, 0.0f};
+
+    printf("{\"renderer\": \"%s\", \"version\": \"%s\", \"mode\": %d, \"frame_s\": [", glGetString(GL_RENDERER),
+           glGetString(GL_VERSION), mode);
+    for (int r = 0; r < repeat; r++)
+    {
+        double t0 = now();
+        glViewport(0, 0, (GLsizei) ow, (GLsizei) oh); /* L288 */
+        glClearColor(0.0f, 0.0f, 0.0f, 0.0f);
+        glClear(GL_COLOR_BUFFER_BIT | GL_DEPTH_BUFFER_BIT);
+        glBufferData(GL_ARRAY_BUFFER, sizeof(quad), quad, GL_DYNAMIC_DRAW);
+        glDrawArrays(GL_TRIANGLES, 0, 6);
+        glFinish();
+        printf("%s%.6f", r ? ", " : "", now() - t0);
+    }
+    printf("], \"gl_error\": %u}\n", glGetError());
+
+    unsigned char* out = malloc((size_t) W * H * 4);
+    glReadPixels(0, 0, W, H, GL_RGBA, GL_UNSIGNED_BYTE, out);
+    f = fopen(argv[2], "wb");
+    if (!f) die("cannot open output");
+    fwrite(out, 4, (size_t) W * H, f);
+    fclose(f);
+    return 0;
+}
