@@ -291,13 +291,18 @@ int main(int argc, char** argv)
     fsh[fl] = 0;
     memcpy(vsh, _binary_octree_vsh_c_start, vl);
     vsh[vl] = 0;
-    const char* pack = "{ int qv = floatBitsToInt(qb_out); fragColor = vec4(float(qv & 255) / 255.0, "
+    const char* pack = "{ int qv = floatBitsToInt(qb_keep); fragColor = vec4(float(qv & 255) / 255.0, "
                        "float((qv >> 8) & 255) / 255.0, float((qv >> 16) & 255) / 255.0, "
                        "float((qv >> 24) & 255) / 255.0); }";
     if (mode != 0)
     {
-        fsh = patch(fsh, "out vec4 fragColor;", "out vec4 fragColor;\nfloat qb_out = intBitsToFloat(-1);");
+        /* qb_out is written at the leaf of whichever trace ran last; qb_keep latches the PRIMARY trace's value */
+        fsh = patch(fsh, "out vec4 fragColor;",
+                    "out vec4 fragColor;\nfloat qb_out = intBitsToFloat(-1);\nfloat qb_keep = intBitsToFloat(-1);");
         fsh = patch(fsh, "fragColor = col;", pack);
+        if (mode == 1 || mode == 2)
+            fsh = patch(fsh, "ctlres res = cube_trace_line(camfp, csv);",
+                        "ctlres res = cube_trace_line(camfp, csv);\nqb_keep = qb_out;");
     }
     if (mode == 1)
         fsh = patch(fsh, "int docti = oct_from_octets_for_index(8, stck[level].docti, octtexbuf_d, level);",
@@ -308,7 +313,7 @@ int main(int argc, char** argv)
                     "int docti = oct_from_octets_for_index(8, stck[level].docti, octtexbuf_d, level);\n"
                     "qb_out = intBitsToFloat(docti);");
     if (mode == 3)
-        fsh = patch(fsh, "col.z *= 0.7;", "col.z *= 0.7;\nqb_out = intBitsToFloat(int(step(sqr, 15.0)));");
+        fsh = patch(fsh, "col.z *= 0.7;", "col.z *= 0.7;\nqb_keep = intBitsToFloat(int(step(sqr, 15.0)));");
 
     GLuint prog = glCreateProgram();
     glAttachShader(prog, compile(GL_VERTEX_SHADER, vsh));

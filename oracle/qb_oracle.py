@@ -230,3 +230,50 @@ class RefOctree:
             self.l.qbref_tree_delete(self.h)
         except Exception:
             pass
+
+
+# ---------------------------------------------------------------------------
+# the reference's unmodified GLSL on Mesa llvmpipe (oracle/_ref/glsl_ref), when available
+# ---------------------------------------------------------------------------
+
+def have_glsl():
+    return os.path.exists(REF_GLSL) and os.path.exists(
+        os.environ.get("QB_MESA_LIBGL",
+                       "/opt/nvidia/nsight-compute/2025.2.1/host/linux-desktop-glibc_2_11_3-x64/Mesa/libGL.so.1"))
+
+
+def glsl_render(scene, u, mode=0, repeat=1, threads=None, workdir=None):
+    """Run the reference shader for the uniforms `u`; returns (uint8 [H,W,4], info dict).
+    mode 0 = shader as shipped; 1/2/3 = aux dumps (static model index, dynamic model index, shadow bit)
+    returned as int32 [H,W] decoded from the RGBA8 bytes."""
+    import json
+    import tempfile
+    W, H = u.vp_w, u.vp_h
+    hdr = np.array([len(scene.oct_s), len(scene.oct_d), len(scene.col_s), len(scene.col_d), W, H, u.maxlevel,
+                    u.shoot], dtype=np.int64)
+    uf = np.zeros(16, dtype=np.float32)
+    uf[0:3] = list(u.camfp)
+    uf[3:6] = list(u.angle_in)
+    uf[6:9] = list(u.light)
+    uf[9:13] = list(u.basecube)
+    uf[13:15] = list(u.dimensions)
+    with tempfile.TemporaryDirectory(dir=workdir) as d:
+        fin, fout = os.path.join(d, "in.bin"), os.path.join(d, "out.rgba")
+        with open(fin, "wb") as f:
+            f.write(hdr.tobytes())
+            f.write(uf.tobytes())
+            for a, dt in ((scene.oct_s, np.int32), (scene.oct_d, np.int32), (scene.col_s, np.float32),
+                          (scene.nrm_s, np.float32), (scene.col_d, np.float32), (scene.nrm_d, np.float32)):
+                f.write(np.ascontiguousarray(a, dtype=dt).tobytes())
+        env = dict(os.environ)
+        if threads is not None:
+            env["LP_NUM_THREADS"] = str(int(threads))
+        r = subprocess.run([REF_GLSL, fin, fout, str(mode), str(repeat)], stdout=subprocess.PIPE,
+                           stderr=subprocess.PIPE, text=True, env=env)
+        if r.returncode != 0:
+            raise RuntimeError("glsl_ref failed (%d): %s" % (r.returncode, r.stderr[-2000:]))
+        info = json.loads(r.stdout.strip().splitlines()[-1])
+        out = np.fromfile(fout, dtype=np.uint8).reshape(H, W, 4)
+    if mode != 0:
+        out = out.view(np.int32).reshape(H, W)
+    return out, info
