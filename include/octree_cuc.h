@@ -212,6 +212,11 @@ void     octree_cuc_ipc_close(octree_glc_t* rc, uint64_t device_ptr);
 size_t octree_cuc_export_pending(octree_glc_t* rc, void* blob_host, size_t capacity);
 void   octree_cuc_apply_blob(octree_glc_t* rc, const void* blob_host, size_t bytes);
 
+/* device self-test: the fast kernel's hoisted-reciprocal division against the IEEE
+ * `/` on `count` operand pairs drawn like the traversal's (see octree_trace_fast.cuh);
+ * returns the number of results that differ (must be 0) */
+uint64_t octree_cuc_selftest_div(octree_glc_t* rc, uint64_t seed, uint64_t count);
+
 /* library self-description */
 const char* octree_cuc_version(void);
 

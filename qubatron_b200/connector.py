@@ -77,6 +77,7 @@ _PROTOS = {
     "octree_cuc_ipc_export_frame": (None, [C.POINTER(octree_glc_t), C.c_void_p]),
     "octree_cuc_ipc_open": (C.c_uint64, [C.POINTER(octree_glc_t), C.c_void_p]),
     "octree_cuc_ipc_close": (None, [C.POINTER(octree_glc_t), C.c_uint64]),
+    "octree_cuc_selftest_div": (C.c_uint64, [C.POINTER(octree_glc_t), C.c_uint64, C.c_uint64]),
     "octree_cuc_export_pending": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_void_p, C.c_size_t]),
     "octree_cuc_apply_blob": (None, [C.POINTER(octree_glc_t), C.c_void_p, C.c_size_t]),
     "octree_cuc_version": (C.c_char_p, []),
@@ -257,6 +258,9 @@ class OctreeGlc:
 
     def ipc_close(self, ptr):
         self.lib.octree_cuc_ipc_close(self._p, int(ptr))
+
+    def selftest_div(self, seed, count):
+        return int(self.lib.octree_cuc_selftest_div(self._p, int(seed), int(count)))
 
     def export_pending(self):
         need = self.lib.octree_cuc_export_pending(self._p, None, 0)

@@ -46,6 +46,34 @@ using namespace qb;
 // octree_types.cuh.  Both kernels move 4-byte words.
 // ---------------------------------------------------------------------------
 
+// one 32-bit word of the reference node array -> traversal layout.  Child words
+// keep the index in bits 0-27; the node's child-exists mask lives in the top
+// nibble of words 0 and 1 (octree_types.cuh).  Atomics on disjoint bit fields make
+// concurrent updates of one node by several threads safe.
+__device__ __forceinline__ void put_node_word(int* child, int* model, size_t node, int slot, int v)
+{
+    if (slot < 8)
+    {
+        const unsigned idx  = v > 0 ? ((unsigned) v & CHILD_INDEX_MASK) : 0u;
+        unsigned*      w    = (unsigned*) child + node * 8 + slot;
+        unsigned*      mw   = (unsigned*) child + node * 8 + (slot >> 2);
+        const unsigned bit  = 1u << (CHILD_MASK_SHIFT + (slot & 3));
+        if (slot < 2)
+        {
+            atomicAnd(w, ~CHILD_INDEX_MASK);
+            atomicOr(w, idx);
+        }
+        else
+            *w = idx;
+        if (v > 0)
+            atomicOr(mw, bit);
+        else
+            atomicAnd(mw, ~bit);
+    }
+    else if (slot == 8)
+        model[node] = v;
+}
+
 // words [first_word, first_word + nwords) of a 12-int node array -> child/model
 __global__ void relayout_octree_kernel(const int* __restrict__ src, size_t first_word, size_t nwords,
                                        int* __restrict__ child, int* __restrict__ model)
@@ -54,12 +82,25 @@ __global__ void relayout_octree_kernel(const int* __restrict__ src, size_t first
     if (i >= nwords) return;
     size_t k    = first_word + i;
     size_t node = k / 12;
-    int    slot = (int) (k - node * 12);
-    int    v    = src[i];
-    if (slot < 8)
-        child[node * 8 + slot] = v;
-    else if (slot == 8)
-        model[node] = v;
+    put_node_word(child, model, node, (int) (k - node * 12), src[i]);
+}
+
+// whole nodes (the common bulk case): one thread converts one 48-byte node
+__global__ void relayout_octree_nodes_kernel(const int4* __restrict__ src, size_t first_node, size_t nnodes,
+                                             int4* __restrict__ child, int* __restrict__ model)
+{
+    size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+    if (i >= nnodes) return;
+    int4 a = src[3 * i], b = src[3 * i + 1], c = src[3 * i + 2];
+    unsigned m = (a.x > 0 ? 1u : 0u) | (a.y > 0 ? 2u : 0u) | (a.z > 0 ? 4u : 0u) | (a.w > 0 ? 8u : 0u) |
+                 (b.x > 0 ? 16u : 0u) | (b.y > 0 ? 32u : 0u) | (b.z > 0 ? 64u : 0u) | (b.w > 0 ? 128u : 0u);
+    auto ix = [](int v) { return v > 0 ? (int) ((unsigned) v & CHILD_INDEX_MASK) : 0; };
+    int4 lo = make_int4(ix(a.x) | (int) ((m & 15u) << CHILD_MASK_SHIFT), ix(a.y) | (int) ((m >> 4) << CHILD_MASK_SHIFT),
+                        ix(a.z), ix(a.w));
+    int4 hi = make_int4(ix(b.x), ix(b.y), ix(b.z), ix(b.w));
+    child[2 * (first_node + i)]     = lo;
+    child[2 * (first_node + i) + 1] = hi;
+    model[first_node + i]           = c.x;
 }
 
 // words of a float[3] array -> 32-byte point records; which = 0 colour, 1 normal
@@ -115,11 +156,7 @@ __global__ void scatter_ranges_kernel(const RangeDesc* __restrict__ descs, int n
         {
             int    t    = d.buftype == OCTREE_GLC_BUFFER_DYNAMIC_OCTREE;
             size_t node = k / 12;
-            int    slot = (int) (k - node * 12);
-            if (slot < 8)
-                T.child[t][node * 8 + slot] = v;
-            else if (slot == 8)
-                T.model[t][node] = v;
+            put_node_word(T.child[t], T.model[t], node, (int) (k - node * 12), v);
             break;
         }
         default:
@@ -159,7 +196,7 @@ struct Points
     size_t   points     = 0;
 };
 
-constexpr size_t STAGE_BYTES   = 64u << 20; // device staging chunk for bulk uploads
+constexpr size_t STAGE_BYTES   = 48u * 1398101u; // ~64 MiB device staging chunk, a whole number of nodes and points
 constexpr size_t BATCH_BYTES   = 8u << 20;  // pinned staging for small ranges
 constexpr size_t BATCH_MAXDESC = 1u << 16;
 constexpr size_t SMALL_RANGE   = 256u << 10; // ranges up to this size are batched
@@ -317,6 +354,7 @@ bool ensure_capacity(Impl* I, int buftype, size_t size)
     {
         Tree&  T     = I->tree[t];
         size_t nodes = (size + 47) / 48;
+        if (nodes > (size_t) CHILD_INDEX_MASK + 1) die("octree arrays are limited to 2^28 nodes per tree");
         if (nodes <= T.cap_nodes) return false;
         flush_pending(I);
         size_t cap = grown(nodes);
@@ -361,7 +399,13 @@ void upload_bulk(Impl* I, const char* data, int buftype, size_t s, size_t e)
         CUDA_OK(cudaMemcpyAsync(I->stage_dev, data + off, n, cudaMemcpyHostToDevice, I->stream));
         size_t   words  = n / 4;
         unsigned blocks = (unsigned) ((words + 255) / 256);
-        if (is_octree(buftype))
+        if (is_octree(buftype) && off % 48 == 0 && n % 48 == 0)
+        {
+            size_t nn = n / 48;
+            relayout_octree_nodes_kernel<<<(unsigned) ((nn + 255) / 256), 256, 0, I->stream>>>(
+                (const int4*) I->stage_dev, off / 48, nn, (int4*) I->tree[t].child.ptr, (int*) I->tree[t].model.ptr);
+        }
+        else if (is_octree(buftype))
             relayout_octree_kernel<<<blocks, 256, 0, I->stream>>>((const int*) I->stage_dev, off / 4, words,
                                                                   (int*) I->tree[t].child.ptr,
                                                                   (int*) I->tree[t].model.ptr);
@@ -1026,6 +1070,19 @@ void octree_cuc_ipc_close(octree_glc_t* rc, uint64_t device_ptr)
     CUDA_OK(cudaStreamSynchronize(I->stream));
     if (I->ext_target == device_ptr) I->ext_target = 0;
     CUDA_OK(cudaIpcCloseMemHandle((void*) (uintptr_t) device_ptr));
+}
+
+uint64_t octree_cuc_selftest_div(octree_glc_t* rc, uint64_t seed, uint64_t count)
+{
+    Impl* I = impl_of(rc);
+    CUDA_OK(cudaMemsetAsync(I->counters, 0, sizeof(unsigned long long), I->stream));
+    selftest_div_kernel<<<148 * 8, 256, 0, I->stream>>>(seed, count, I->counters);
+    CUDA_OK(cudaGetLastError());
+    I->launches++;
+    unsigned long long bad = 0;
+    CUDA_OK(cudaMemcpyAsync(&bad, I->counters, sizeof(bad), cudaMemcpyDeviceToHost, I->stream));
+    CUDA_OK(cudaStreamSynchronize(I->stream));
+    return (uint64_t) bad;
 }
 
 // blob = { uint64 ndesc, uint64 payload_bytes, RangeDesc[ndesc], payload }

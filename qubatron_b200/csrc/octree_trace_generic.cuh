@@ -96,6 +96,8 @@ __device__ __forceinline__ Children load_children(const TreeDev& t, int node, in
     {
         c.lo = __ldg(t.child + 2 * (size_t) node);
         c.hi = __ldg(t.child + 2 * (size_t) node + 1);
+        c.lo.x &= (int) CHILD_INDEX_MASK; // words 0/1 carry the child-exists mask in their top nibble
+        c.lo.y &= (int) CHILD_INDEX_MASK;
     }
     return c;
 }

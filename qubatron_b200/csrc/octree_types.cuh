@@ -3,7 +3,13 @@
 // HBM layout (see DESIGN.md "Data layout"):
 //   child_{s,d} : int4[2*nodes]  -- the 8 child indices of a node, 32 B, one
 //                                   aligned sector per node expansion
-//                                   (reference node = int32[12], octree.c L11-14)
+//                                   (reference node = int32[12], octree.c L11-14).
+//                                   Bits 0-27 of a word = child node index
+//                                   (0 = absent); the top 4 bits of words 0 and 1
+//                                   hold the node's 8-bit "child exists" mask
+//                                   (bit k of the mask = child k > 0), maintained by
+//                                   the upload kernels, so an expansion needs 8 bytes
+//                                   of the node and a descent one more word.
 //   model_{s,d} : int32[nodes]   -- oct[8] of the node (point index), split out
 //                                   as the reference author wanted
 //                                   (octree_fsh.c L125)
@@ -90,6 +96,9 @@ struct FrameParams
     const ViewParams* views; // device array, n_views entries
     int               n_views;
 };
+
+constexpr unsigned CHILD_INDEX_MASK = 0x0FFFFFFFu; // 2^28 nodes per tree
+constexpr int      CHILD_MASK_SHIFT = 28;
 
 constexpr int BLOCK_W       = 16; // pixels per CTA in x
 constexpr int BLOCK_H       = 8;  // pixels per CTA in y

@@ -305,3 +305,13 @@ def test_full_size_properties(scene_c1):
     assert np.array_equal(ref["aux"][500:560], f[1][1][500:560])
     assert np.abs(ref["rgba"][500:560].astype(np.int16) - f[0][500:560].astype(np.int16)).max() <= parity.RGB_TOL
     rc.destroy()
+
+
+def test_hoisted_division_equals_ieee_division():
+    """The fast kernel replaces `(c - o) / d` by nvcc's own fast-path FFMA sequence with the reciprocal
+    hoisted out of the loop; on 2 x 200 M operand pairs drawn like the traversal's it must give the IEEE
+    quotient every time (+-0 aside, which no comparison in the traversal can tell apart)."""
+    rc = K.OctreeGlc(b"", device=0)
+    for seed in (1, 2):
+        assert rc.selftest_div(seed, 100_000_000) == 0
+    rc.destroy()
