@@ -175,6 +175,17 @@ void octree_cuc_set_light(octree_glc_t* rc, const float* light_xyz_or_null);
 void octree_cuc_set_kernel(octree_glc_t* rc, int which);
 int  octree_cuc_last_kernel(octree_glc_t* rc);
 
+/* division semantics of the pixel program.  The shader's `/` has two reproducible
+ * executions and the connector can match either bit for bit:
+ *   OCTREE_CUC_DIV_GLSL (default): a / b evaluated as a * (1.0 / b) -- what Mesa's
+ *     GLSL front end makes of it (DIV_TO_MUL_RCP) when the reference shader runs
+ *     headless on llvmpipe;
+ *   OCTREE_CUC_DIV_IEEE: one correctly rounded divide -- what the reference's
+ *     compiled CPU twin octree_trace_line (octree.c L302-339) computes. */
+#define OCTREE_CUC_DIV_GLSL 0
+#define OCTREE_CUC_DIV_IEEE 1
+void octree_cuc_set_division(octree_glc_t* rc, int mode);
+
 /* device time of the last frame's kernels in milliseconds (CUDA events on the
  * connector's stream); synchronises on the frame */
 float octree_cuc_last_frame_ms(octree_glc_t* rc);

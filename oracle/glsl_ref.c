@@ -312,6 +312,13 @@ int main(int argc, char** argv)
         fsh = patch(fsh, "int docti = oct_from_octets_for_index(8, stck[level].docti, octtexbuf_d, level);",
                     "int docti = oct_from_octets_for_index(8, stck[level].docti, octtexbuf_d, level);\n"
                     "qb_out = intBitsToFloat(docti);");
+    if (mode == 9) /* debug: dump any float expression of main() evaluated after the ray set-up (QB_DEBUG_EXPR) */
+    {
+        char buf[512];
+        snprintf(buf, sizeof(buf), "csv = quat_rotate(qx, csv);\nqb_keep = %s;",
+                 getenv("QB_DEBUG_EXPR") ? getenv("QB_DEBUG_EXPR") : "csv.x");
+        fsh = patch(fsh, "csv = quat_rotate(qx, csv);", buf);
+    }
     if (mode == 3)
         fsh = patch(fsh, "col.z *= 0.7;", "col.z *= 0.7;\nqb_keep = intBitsToFloat(int(step(sqr, 15.0)));");
 

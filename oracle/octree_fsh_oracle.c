@@ -26,6 +26,16 @@
     #include <omp.h>
 #endif
 
+/* Division.  Default: IEEE `/`, which is what the reference's own CPU twin (octree.c L302-339, compiled C)
+ * does and what the CUDA path reproduces.  -DQB_DIV_MUL_RCP builds the variant that mirrors Mesa's GLSL
+ * lowering (lower_instructions DIV_TO_MUL_RCP: a / b -> a * (1.0 / b), two roundings), used only to explain
+ * the 0-2 pixels per frame on which llvmpipe and the IEEE oracle differ (tests/test_golden.py). */
+#ifdef QB_DIV_MUL_RCP
+    #define QB_DIV(a, b) ((a) * (1.0f / (b)))
+#else
+    #define QB_DIV(a, b) ((a) / (b))
+#endif
+
 typedef struct f4
 {
     float x, y, z, w;
@@ -78,7 +88,7 @@ static inline f4 plane_hit(int axis, float c, f3 lp, f3 lv)
     {
         if (lv.x != 0.0f)
         {
-            r.w = (c - lp.x) / lv.x;
+            r.w = QB_DIV(c - lp.x, lv.x);
             r.y = lp.y + lv.y * r.w;
             r.z = lp.z + lv.z * r.w;
             r.x = c;
@@ -88,7 +98,7 @@ static inline f4 plane_hit(int axis, float c, f3 lp, f3 lv)
     {
         if (lv.y != 0.0f)
         {
-            r.w = (c - lp.y) / lv.y;
+            r.w = QB_DIV(c - lp.y, lv.y);
             r.x = lp.x + lv.x * r.w;
             r.z = lp.z + lv.z * r.w;
             r.y = c;
@@ -98,7 +108,7 @@ static inline f4 plane_hit(int axis, float c, f3 lp, f3 lv)
     {
         if (lv.z != 0.0f)
         {
-            r.w = (c - lp.z) / lv.z;
+            r.w = QB_DIV(c - lp.z, lv.z);
             r.x = lp.x + lv.x * r.w;
             r.y = lp.y + lv.y * r.w;
             r.z = c;
@@ -357,7 +367,7 @@ static inline float v_dot(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z
 static inline f3    v_normalize(f3 a)
 {
     float l = sqrtf(v_dot(a, a));
-    f3    r = {a.x / l, a.y / l, a.z / l};
+    f3    r = {QB_DIV(a.x, l), QB_DIV(a.y, l), QB_DIV(a.z, l)};
     return r;
 }
 
@@ -539,7 +549,7 @@ static void shade_pixel(const qb_scene* sc, const qb_uniforms* u, const frame_co
         else
         {
             float resvx = lcres.isp.x - fc->camfp.x;
-            if (resvx / lghtv.x > 1.0f)
+            if (QB_DIV(resvx, lghtv.x) > 1.0f)
             {
                 flags |= QB_FLAG_DISC_ON;
                 col.x = col.y = col.z = col.w = 1.0f;

@@ -11,7 +11,9 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-ORACLE_SO = os.path.join(HERE, "liboctree_fsh_oracle.so")
+ORACLE_SO = os.path.join(HERE, "liboctree_fsh_oracle.so")            # IEEE division (reference CPU twin)
+ORACLE_GLSL_SO = os.path.join(HERE, "liboctree_fsh_oracle_glsl.so")  # a * (1/b) (reference GLSL on llvmpipe)
+DIV_GLSL, DIV_IEEE = 0, 1
 REF_SO = os.path.join(HERE, "_ref", "libqubatron_ref.so")
 REF_QMC = os.path.join(HERE, "_ref", "qmc")
 REF_GLSL = os.path.join(HERE, "_ref", "glsl_ref")
@@ -54,15 +56,16 @@ def algorithmic_bytes(c, pixels):
     return 32 * (c["expand_s"] + c["expand_d"]) + 4 * (c["leaf_s"] + c["leaf_d"]) + 24 * c["hits"] + 4 * pixels
 
 
-_lib = None
+_libs = {}
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        if not os.path.exists(ORACLE_SO):
+def lib(div=DIV_GLSL):
+    """The oracle library for one division semantics (see oracle/Makefile)."""
+    if div not in _libs:
+        path = ORACLE_GLSL_SO if div == DIV_GLSL else ORACLE_SO
+        if not os.path.exists(path):
             build(ref=False)
-        l = C.CDLL(ORACLE_SO)
+        l = C.CDLL(path)
         l.qb_oracle_uniforms.argtypes = [C.POINTER(Uniforms), C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_float,
                                          C.c_uint8, C.c_int, C.c_float, C.c_int]
         l.qb_oracle_render.argtypes = [C.POINTER(_Scene), C.POINTER(Uniforms), C.c_int, C.c_int, C.c_void_p,
@@ -70,8 +73,8 @@ def lib():
         l.qb_oracle_trace_batch.argtypes = [C.POINTER(_Scene), C.POINTER(Uniforms), C.c_int64, C.c_void_p, C.c_void_p,
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         l.qb_oracle_pixel_ray.argtypes = [C.POINTER(Uniforms), C.c_int, C.c_int, C.c_void_p]
-        _lib = l
-    return _lib
+        _libs[div] = l
+    return _libs[div]
 
 
 def _ptr(a):
@@ -108,7 +111,7 @@ def uniforms(width, height, position, angle, lighta=0.0, quality=10, maxlevel=12
     return u
 
 
-def render(oscene, u, rows=None, threads=0, want_aux=True):
+def render(oscene, u, rows=None, threads=0, want_aux=True, div=DIV_GLSL):
     """Returns dict(rgba [H,W,4] u8, flags [H,W] u8, aux [H,W,6] i32, counters dict)."""
     W, H = u.vp_w, u.vp_h
     rgba = np.zeros((H, W, 4), dtype=np.uint8)
@@ -116,12 +119,12 @@ def render(oscene, u, rows=None, threads=0, want_aux=True):
     aux = np.full((H, W, AUX_STRIDE), -1, dtype=np.int32) if want_aux else None
     cnt = Counters()
     r0, r1 = (0, H) if rows is None else rows
-    lib().qb_oracle_render(C.byref(oscene.c), C.byref(u), int(r0), int(r1), _ptr(rgba), _ptr(flags), _ptr(aux),
-                           C.byref(cnt), int(threads))
+    lib(div).qb_oracle_render(C.byref(oscene.c), C.byref(u), int(r0), int(r1), _ptr(rgba), _ptr(flags), _ptr(aux),
+                              C.byref(cnt), int(threads))
     return {"rgba": rgba, "flags": flags, "aux": aux, "counters": cnt.as_dict()}
 
 
-def trace_batch(oscene, u, pos, direction, threads=0):
+def trace_batch(oscene, u, pos, direction, threads=0, div=DIV_GLSL):
     pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 3)
     direction = np.ascontiguousarray(direction, dtype=np.float32).reshape(-1, 3)
     n = len(pos)
@@ -129,8 +132,8 @@ def trace_batch(oscene, u, pos, direction, threads=0):
     nodes = np.zeros((n, 2), dtype=np.int32)
     models = np.zeros((n, 2), dtype=np.int32)
     isp = np.zeros((n, 4), dtype=np.float32)
-    lib().qb_oracle_trace_batch(C.byref(oscene.c), C.byref(u), n, _ptr(pos), _ptr(direction), _ptr(result),
-                                _ptr(nodes), _ptr(models), _ptr(isp), int(threads))
+    lib(div).qb_oracle_trace_batch(C.byref(oscene.c), C.byref(u), n, _ptr(pos), _ptr(direction), _ptr(result),
+                                   _ptr(nodes), _ptr(models), _ptr(isp), int(threads))
     return result, nodes, models, isp
 
 

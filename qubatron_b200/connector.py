@@ -28,6 +28,7 @@ AUX_MODEL_S, AUX_MODEL_D, AUX_NODE_S, AUX_NODE_D, AUX_SH_NODE_S, AUX_SH_NODE_D =
 AUX_STRIDE = 6
 
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FAST = 0, 1, 2
+DIV_GLSL, DIV_IEEE = 0, 1
 
 
 class v3_t(C.Structure):
@@ -68,6 +69,7 @@ _PROTOS = {
     "octree_cuc_set_light": (None, [C.POINTER(octree_glc_t), C.c_void_p]),
     "octree_cuc_set_kernel": (None, [C.POINTER(octree_glc_t), C.c_int]),
     "octree_cuc_last_kernel": (C.c_int, [C.POINTER(octree_glc_t)]),
+    "octree_cuc_set_division": (None, [C.POINTER(octree_glc_t), C.c_int]),
     "octree_cuc_last_frame_ms": (C.c_float, [C.POINTER(octree_glc_t)]),
     "octree_cuc_launch_count": (C.c_uint64, [C.POINTER(octree_glc_t)]),
     "octree_cuc_update_views": (None, [C.POINTER(octree_glc_t), C.c_int, C.c_float, C.c_float, C.c_void_p,
@@ -220,6 +222,10 @@ class OctreeGlc:
 
     def set_kernel(self, which):
         self.lib.octree_cuc_set_kernel(self._p, int(which))
+
+    def set_division(self, mode):
+        """DIV_GLSL (default): a*(1/b) like the reference shader on llvmpipe; DIV_IEEE: like the CPU twin."""
+        self.lib.octree_cuc_set_division(self._p, int(mode))
 
     def last_kernel(self):
         return int(self.lib.octree_cuc_last_kernel(self._p))

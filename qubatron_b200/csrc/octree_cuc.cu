@@ -248,6 +248,7 @@ struct Impl
     float light[3]       = {0, 0, 0};
     int   kernel_choice  = 0;
     int   last_kernel    = 0;
+    int   div_mode       = DIV_GLSL; // division semantics, octree_trace_generic.cuh
 
     uint64_t launches = 0;
     uint64_t memsize  = 0;
@@ -574,48 +575,60 @@ void fill_view(Impl* I, ViewParams& V, float ow, const float* position, const fl
     volatile float s1 = xx + yy;
     volatile float s2 = s1 + zz;
     float          l  = sqrtf(s2);
+    volatile float inv = 1.0f / l;
     for (int i = 0; i < 3; i++)
     {
-        volatile float q = cl[i] / l;
+        // normalize(): v * (1/len) under the GLSL lowering, v / len with IEEE division
+        volatile float q = I->div_mode == DIV_GLSL ? cl[i] * inv : cl[i] / l;
         V.camlight_n[i]  = q;
     }
     V.disc_dot_min = disc_dot_min();
     V.shoot        = shoot;
 }
 
-void launch_generic(Impl* I, const FrameParams& P, unsigned blocks)
+template <int DIV>
+void launch_generic_div(Impl* I, const FrameParams& P, unsigned blocks)
 {
     if (I->aux_on && I->count_on)
-        render_kernel<GenericTracer, true, true><<<blocks, BLOCK_THREADS, 0, I->stream>>>(P);
+        render_kernel<GenericTracer<DIV>, true, true><<<blocks, BLOCK_THREADS, 0, I->stream>>>(P);
     else if (I->aux_on)
-        render_kernel<GenericTracer, true, false><<<blocks, BLOCK_THREADS, 0, I->stream>>>(P);
+        render_kernel<GenericTracer<DIV>, true, false><<<blocks, BLOCK_THREADS, 0, I->stream>>>(P);
     else if (I->count_on)
-        render_kernel<GenericTracer, false, true><<<blocks, BLOCK_THREADS, 0, I->stream>>>(P);
+        render_kernel<GenericTracer<DIV>, false, true><<<blocks, BLOCK_THREADS, 0, I->stream>>>(P);
     else
-        render_kernel<GenericTracer, false, false><<<blocks, BLOCK_THREADS, 0, I->stream>>>(P);
+        render_kernel<GenericTracer<DIV>, false, false><<<blocks, BLOCK_THREADS, 0, I->stream>>>(P);
 }
 
-template <bool DYN>
+void launch_generic(Impl* I, const FrameParams& P, unsigned blocks)
+{
+    if (I->div_mode == DIV_GLSL)
+        launch_generic_div<DIV_GLSL>(I, P, blocks);
+    else
+        launch_generic_div<DIV_IEEE>(I, P, blocks);
+}
+
+template <int DIV, bool DYN>
 void launch_fast_dyn(Impl* I, const FrameParams& P, unsigned blocks)
 {
     const size_t smem = (size_t) 3 * P.maxlevel * BLOCK_THREADS * sizeof(int);
     if (I->aux_on && I->count_on)
-        render_fast_kernel<DYN, true, true><<<blocks, BLOCK_THREADS, smem, I->stream>>>(P);
+        render_fast_kernel<DIV, DYN, true, true><<<blocks, BLOCK_THREADS, smem, I->stream>>>(P);
     else if (I->aux_on)
-        render_fast_kernel<DYN, true, false><<<blocks, BLOCK_THREADS, smem, I->stream>>>(P);
+        render_fast_kernel<DIV, DYN, true, false><<<blocks, BLOCK_THREADS, smem, I->stream>>>(P);
     else if (I->count_on)
-        render_fast_kernel<DYN, false, true><<<blocks, BLOCK_THREADS, smem, I->stream>>>(P);
+        render_fast_kernel<DIV, DYN, false, true><<<blocks, BLOCK_THREADS, smem, I->stream>>>(P);
     else
-        render_fast_kernel<DYN, false, false><<<blocks, BLOCK_THREADS, smem, I->stream>>>(P);
+        render_fast_kernel<DIV, DYN, false, false><<<blocks, BLOCK_THREADS, smem, I->stream>>>(P);
 }
 
 void launch_fast(Impl* I, const FrameParams& P, unsigned blocks)
 {
     // a dynamic tree that is only a root (octree_reset, octree.c L89-93) has no geometry
-    if (P.tree_d.nodes > 1)
-        launch_fast_dyn<true>(I, P, blocks);
+    const bool dyn = P.tree_d.nodes > 1;
+    if (I->div_mode == DIV_GLSL)
+        dyn ? launch_fast_dyn<DIV_GLSL, true>(I, P, blocks) : launch_fast_dyn<DIV_GLSL, false>(I, P, blocks);
     else
-        launch_fast_dyn<false>(I, P, blocks);
+        dyn ? launch_fast_dyn<DIV_IEEE, true>(I, P, blocks) : launch_fast_dyn<DIV_IEEE, false>(I, P, blocks);
 }
 
 void render_views(octree_glc_t* rc, int n, float width, float height, const float* positions, const float* angles,
@@ -1004,6 +1017,12 @@ void octree_cuc_set_kernel(octree_glc_t* rc, int which)
 }
 
 int octree_cuc_last_kernel(octree_glc_t* rc) { return impl_of(rc)->last_kernel; }
+
+void octree_cuc_set_division(octree_glc_t* rc, int mode)
+{
+    if (mode != DIV_GLSL && mode != DIV_IEEE) die("set_division: 0 = GLSL a*(1/b), 1 = IEEE a/b");
+    impl_of(rc)->div_mode = mode;
+}
 
 float octree_cuc_last_frame_ms(octree_glc_t* rc)
 {

@@ -17,9 +17,15 @@ __device__ __forceinline__ float3 cross3(float3 a, float3 b)
     return make_float3(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y);
 }
 __device__ __forceinline__ float dot3(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+template <int DIV>
 __device__ __forceinline__ float3 normalize3(float3 a)
 {
-    float l = sqrtf(dot3(a, a));
+    const float l = sqrtf(dot3(a, a));
+    if (DIV == DIV_GLSL)
+    {
+        const float inv = 1.0f / l;
+        return make_float3(a.x * inv, a.y * inv, a.z * inv);
+    }
     return make_float3(a.x / l, a.y / l, a.z / l);
 }
 // octree_fsh.c L392-395
@@ -39,12 +45,14 @@ __device__ __forceinline__ unsigned int unorm8(float v)
     return (unsigned int) __float2int_rn(v * 255.0f);
 }
 
+template <int DIV>
 struct GenericTracer
 {
+    static constexpr int div_mode = DIV;
     template <bool COUNT>
     static __device__ __forceinline__ TraceResult trace(const FrameParams& P, float3 pos, float3 dir, RayCounters& c)
     {
-        return trace_generic<COUNT>(P, pos, dir, c);
+        return trace_generic<DIV, COUNT>(P, pos, dir, c);
     }
 };
 
@@ -60,6 +68,7 @@ __device__ __forceinline__ void block_pixel(int tid, int& lx, int& ly)
 template <class TRACER, bool AUX, bool COUNT>
 __global__ void __launch_bounds__(BLOCK_THREADS) render_kernel(const FrameParams P)
 {
+    constexpr int DIV = TRACER::div_mode;
     // CTA -> (view, shard tile, block inside the tile)
     const int blocks_per_tile = P.blocks_per_tile_x * P.blocks_per_tile_y;
     int       b               = blockIdx.x;
@@ -98,7 +107,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) render_kernel(const FrameParams
         csv        = quat_rotate(V.qx, csv);
 
         // L417-418; acos(d) < 0.02 is evaluated as d >= disc_dot_min (host libm threshold)
-        const float3 csv_n  = normalize3(csv);
+        const float3 csv_n  = normalize3<DIV>(csv);
         const float  camdot = dot3(make_float3(V.camlight_n[0], V.camlight_n[1], V.camlight_n[2]), csv_n);
         const bool   disc   = camdot >= V.disc_dot_min && camdot <= 1.0f;
 
@@ -156,9 +165,9 @@ __global__ void __launch_bounds__(BLOCK_THREADS) render_kernel(const FrameParams
                     const float dx = lc.ix - res.ix, dy = lc.iy - res.iy, dz = lc.iz - res.iz;
                     const float sqr = dx * dx + dy * dy + dz * dz;
 
-                    const float3 nn  = normalize3(make_float3(nrm.x, nrm.y, nrm.z));
-                    const float3 nl  = normalize3(make_float3(-lghtv.x, -lghtv.y, -lghtv.z));
-                    const float3 nc  = normalize3(make_float3(-csv.x, -csv.y, -csv.z));
+                    const float3 nn  = normalize3<DIV>(make_float3(nrm.x, nrm.y, nrm.z));
+                    const float3 nl  = normalize3<DIV>(make_float3(-lghtv.x, -lghtv.y, -lghtv.z));
+                    const float3 nc  = normalize3<DIV>(make_float3(-csv.x, -csv.y, -csv.z));
                     const float  lna = max0(dot3(nl, nn));
                     const float  cna = max0(dot3(nc, nn));
                     const float  vis = (15.0f < sqr) ? 0.0f : 1.0f; // step(sqr, 15.0)
@@ -188,7 +197,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) render_kernel(const FrameParams
             else
             {
                 const float resvx = lc.ix - camfp.x;
-                if (resvx / lghtv.x > 1.0f)
+                if (qdiv<DIV>(resvx, lghtv.x) > 1.0f)
                 {
                     flags |= 32;
                     cr = cg = cb = ca = 1.0f;

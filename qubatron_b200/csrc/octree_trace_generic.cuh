@@ -30,39 +30,59 @@ struct RayCounters
     unsigned int v[CNT_COUNT];
 };
 
+// Division semantics.  The reference's `/` has two reproducible executions:
+//   DIV_GLSL: Mesa lowers the shader's a / b to a * (1.0 / b) (lower_instructions
+//             DIV_TO_MUL_RCP; llvmpipe evaluates 1.0 / b with an IEEE divide): two
+//             roundings.  This is what the reference SHADER computes when run
+//             headless, and the connector's default.
+//   DIV_IEEE: one correctly rounded divide, what the reference's compiled CPU twin
+//             octree_trace_line (octree.c L302-339) computes.
+constexpr int DIV_GLSL = 0;
+constexpr int DIV_IEEE = 1;
+
+template <int DIV>
+__device__ __forceinline__ float qdiv(float n, float d)
+{
+    if (DIV == DIV_GLSL) return n * (1.0f / d);
+    return n / d;
+}
+
 // ray / axis-plane intersection (octree_fsh.c L62-99): w = (c - o)/d, the other
 // two coordinates o + d*w, the plane coordinate exactly c.  A ray parallel to
 // the plane yields FLT_MAX in every component so all range tests fail.
+template <int DIV>
 __device__ __forceinline__ float4 plane_hit_x(float c, float3 o, float3 d)
 {
     float4 r = make_float4(FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX);
     if (d.x != 0.0f)
     {
-        r.w = (c - o.x) / d.x;
+        r.w = qdiv<DIV>(c - o.x, d.x);
         r.y = o.y + d.y * r.w;
         r.z = o.z + d.z * r.w;
         r.x = c;
     }
     return r;
 }
+template <int DIV>
 __device__ __forceinline__ float4 plane_hit_y(float c, float3 o, float3 d)
 {
     float4 r = make_float4(FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX);
     if (d.y != 0.0f)
     {
-        r.w = (c - o.y) / d.y;
+        r.w = qdiv<DIV>(c - o.y, d.y);
         r.x = o.x + d.x * r.w;
         r.z = o.z + d.z * r.w;
         r.y = c;
     }
     return r;
 }
+template <int DIV>
 __device__ __forceinline__ float4 plane_hit_z(float c, float3 o, float3 d)
 {
     float4 r = make_float4(FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX);
     if (d.z != 0.0f)
     {
-        r.w = (c - o.z) / d.z;
+        r.w = qdiv<DIV>(c - o.z, d.z);
         r.x = o.x + d.x * r.w;
         r.y = o.y + d.y * r.w;
         r.z = c;
@@ -118,6 +138,7 @@ __device__ __forceinline__ int model_of(const TreeDev& t, int node, int level)
 }
 
 // base-cube entry (octree_fsh.c L157-211).  Returns false on `discard`.
+template <int DIV>
 __device__ __forceinline__ bool base_cube_entry(const float* basecube, float3 pos, float3 dir, float4& entry)
 {
     Cube c;
@@ -139,12 +160,12 @@ __device__ __forceinline__ bool base_cube_entry(const float* basecube, float3 po
         if (hitc == 1) h1 = act;                                                                                      \
         hitc++;                                                                                                       \
     }
-    QB_FACE(plane_hit_z(c.z1, pos, dir), in_x(c, act.x) && in_y(c, act.y)) // front
-    QB_FACE(plane_hit_z(c.z0, pos, dir), in_x(c, act.x) && in_y(c, act.y)) // back
-    QB_FACE(plane_hit_x(c.x0, pos, dir), in_y(c, act.y) && in_z(c, act.z)) // left
-    QB_FACE(plane_hit_x(c.x1, pos, dir), in_y(c, act.y) && in_z(c, act.z)) // right
-    QB_FACE(plane_hit_y(c.y1, pos, dir), in_x(c, act.x) && in_z(c, act.z)) // top
-    QB_FACE(plane_hit_y(c.y0, pos, dir), in_x(c, act.x) && in_z(c, act.z)) // bottom
+    QB_FACE(plane_hit_z<DIV>(c.z1, pos, dir), in_x(c, act.x) && in_y(c, act.y)) // front
+    QB_FACE(plane_hit_z<DIV>(c.z0, pos, dir), in_x(c, act.x) && in_y(c, act.y)) // back
+    QB_FACE(plane_hit_x<DIV>(c.x0, pos, dir), in_y(c, act.y) && in_z(c, act.z)) // left
+    QB_FACE(plane_hit_x<DIV>(c.x1, pos, dir), in_y(c, act.y) && in_z(c, act.z)) // right
+    QB_FACE(plane_hit_y<DIV>(c.y1, pos, dir), in_x(c, act.x) && in_z(c, act.z)) // top
+    QB_FACE(plane_hit_y<DIV>(c.y0, pos, dir), in_x(c, act.x) && in_z(c, act.z)) // bottom
 #undef QB_FACE
 
     if (hitc < 2) return false;                   // L195
@@ -169,7 +190,7 @@ struct GenericLevel
 
 constexpr int GENERIC_STACK = 18; // octree_fsh.c L151
 
-template <bool COUNT>
+template <int DIV, bool COUNT>
 __device__ __noinline__ TraceResult trace_generic(const FrameParams& P, float3 pos, float3 dir, RayCounters& cnt)
 {
     TraceResult res;
@@ -179,7 +200,7 @@ __device__ __noinline__ TraceResult trace_generic(const FrameParams& P, float3 p
     res.model_s = res.model_d = 0;
 
     float4 entry;
-    if (!base_cube_entry(P.basecube, pos, dir, entry))
+    if (!base_cube_entry<DIV>(P.basecube, pos, dir, entry))
     {
         res.status = -1;
         return res;
@@ -255,11 +276,11 @@ __device__ __noinline__ TraceResult trace_generic(const FrameParams& P, float3 p
             int    hc = 1;
             hp[0]     = stck[level].isps[0];
             float4 act;
-            act = plane_hit_z(hz, pos, dir);
+            act = plane_hit_z<DIV>(hz, pos, dir);
             if (act.w > 0.0f && in_x(c, act.x) && in_y(c, act.y)) hp[hc++] = act;
-            act = plane_hit_x(hx, pos, dir);
+            act = plane_hit_x<DIV>(hx, pos, dir);
             if (act.w > 0.0f && in_y(c, act.y) && in_z(c, act.z)) hp[hc++] = act;
-            act = plane_hit_y(hy, pos, dir);
+            act = plane_hit_y<DIV>(hy, pos, dir);
             if (act.w > 0.0f && in_x(c, act.x) && in_z(c, act.z)) hp[hc++] = act;
 
             int pre  = -1;

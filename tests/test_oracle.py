@@ -17,15 +17,16 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 @pytest.mark.parametrize("pos,ang", [(S.CAMERA_C1[0], S.CAMERA_C1[1]), ((760.0, 160.0, 330.0), (-0.7, -0.35, 0.0)),
                                      ((1200.0, 300.0, 900.0), (-0.9, -0.2, 0.0))])
 def test_trace_equals_reference_cpu_twin(scene_c1, pos, ang):
-    """cube_trace_line restatement vs octree_trace_line (octree.c L341-537), static tree, every pixel's primary ray:
-    same hit mask, same hit model index, same leaf cube."""
+    """cube_trace_line restatement (IEEE-division build, like the compiled C of the reference) vs
+    octree_trace_line (octree.c L341-537), static tree, every pixel's primary ray: same hit mask, same hit model
+    index."""
     ref = O.RefOctree()
     ref.insert_points(scene_c1.pnt_s)
     u = O.uniforms(320, 180, pos, ang)
     rays = O.pixel_rays(u).reshape(-1, 3)
     org = np.tile(np.asarray(pos, np.float32), (len(rays), 1))
     idx, tlf = ref.trace(org, rays)
-    res, nodes, models, isp = O.trace_batch(O.OracleScene(scene_c1), u, org, rays)
+    res, nodes, models, isp = O.trace_batch(O.OracleScene(scene_c1), u, org, rays, div=O.DIV_IEEE)
     leaf = res == 1
     assert leaf.sum() > 500
     assert np.array_equal(idx[leaf], models[leaf, 0])
@@ -41,13 +42,13 @@ def test_shadow_rays_equal_reference_cpu_twin(scene_c1):
     u = O.uniforms(320, 180, *S.CAMERA_C1)
     rays = O.pixel_rays(u).reshape(-1, 3)
     org = np.tile(np.asarray(S.CAMERA_C1[0], np.float32), (len(rays), 1))
-    res, _, _, isp = O.trace_batch(osc, u, org, rays)
+    res, _, _, isp = O.trace_batch(osc, u, org, rays, div=O.DIV_IEEE)
     hit = (res == 1) & (isp[:, 3] > 0)
     light = np.array([u.light[0], u.light[1], u.light[2]], np.float32)
     sdir = (isp[hit, :3] - light[None, :]).astype(np.float32)
     sorg = np.tile(light, (len(sdir), 1))
     idx, _ = ref.trace(sorg, sdir)
-    res2, _, models2, _ = O.trace_batch(osc, u, sorg, sdir)
+    res2, _, models2, _ = O.trace_batch(osc, u, sorg, sdir, div=O.DIV_IEEE)
     leaf = res2 == 1
     assert np.array_equal(idx[leaf], models2[leaf, 0]) and (idx[~leaf] == 0).all()
 

@@ -14,25 +14,33 @@ from qubatron_b200 import scene as S
 pytestmark = pytest.mark.gpu
 
 KERNELS = [(K.KERNEL_GENERIC, "generic"), (K.KERNEL_FAST, "fast")]
+# both reproducible executions of the reference's `/` (include/octree_cuc.h, octree_cuc_set_division)
+DIVS = [(K.DIV_GLSL, O.DIV_GLSL, "glsl"), (K.DIV_IEEE, O.DIV_IEEE, "ieee")]
 
 
-def _render_and_compare(sc, W, H, pos, ang, kernels=KERNELS, rc=None, **kw):
+def _render_and_compare(sc, W, H, pos, ang, kernels=KERNELS, rc=None, divs=DIVS, **kw):
     own = rc is None
     if own:
         rc = K.OctreeGlc(b"", device=0)
         rc.upload_scene(sc)
     rc.enable_aux(True)
     rc.enable_counters(True)
-    ref = O.render(O.OracleScene(sc), O.uniforms(W, H, pos, ang, **kw))
+    osc = O.OracleScene(sc)
     outs = {}
-    for kern, name in kernels:
-        rc.set_kernel(kern)
-        rc.update(W, H, pos, ang, **kw)
-        rgba = rc.read_frame()
-        flags, aux = rc.read_aux()
-        outs[name] = parity.compare(rgba, flags, aux, ref, what=name)
-        assert rc.read_counters() == ref["counters"], name
-        assert rc.last_kernel() == kern
+    ref = None
+    for kdiv, odiv, dname in divs:
+        r = O.render(osc, O.uniforms(W, H, pos, ang, **kw), div=odiv)
+        ref = ref or r
+        rc.set_division(kdiv)
+        for kern, name in kernels:
+            rc.set_kernel(kern)
+            rc.update(W, H, pos, ang, **kw)
+            rgba = rc.read_frame()
+            flags, aux = rc.read_aux()
+            outs[name + "/" + dname] = parity.compare(rgba, flags, aux, r, what=name + "/" + dname)
+            assert rc.read_counters() == r["counters"], name + "/" + dname
+            assert rc.last_kernel() == kern
+    rc.set_division(K.DIV_GLSL)
     if own:
         rc.destroy()
     return ref, outs
@@ -314,4 +322,32 @@ def test_hoisted_division_equals_ieee_division():
     rc = K.OctreeGlc(b"", device=0)
     for seed in (1, 2):
         assert rc.selftest_div(seed, 100_000_000) == 0
+    rc.destroy()
+
+
+@pytest.mark.parametrize("name", __import__("golden_util").CASES)
+def test_golden_frames_of_the_reference_shader(name):
+    """The CUDA path against what the reference's own shader produced on llvmpipe (tests/golden/): in the default
+    (GLSL) division mode both kernels must give the shader's hit voxel indices and shadow bits exactly and its RGBA
+    within +-1/255 -- they give it exactly."""
+    import golden_util
+    sc, args, g = golden_util.load(name)
+    if sc is None:
+        pytest.skip("scene generator gives different bits on this CPU (hash mismatch); embedded cases still run")
+    rc = K.OctreeGlc(b"", device=0)
+    rc.upload_scene(sc)
+    rc.enable_aux(True)
+    for kern, kname in KERNELS:
+        rc.set_kernel(kern)
+        rc.update(args["width"], args["height"], args["position"], args["angle"], args.get("lighta", 0.0),
+                  args.get("quality", 10), args.get("maxlevel", 12), args.get("basesize", 1800.0), args.get("shoot", 0))
+        rgba = rc.read_frame()
+        flags, aux = rc.read_aux()
+        assert np.abs(rgba.astype(np.int16) - g["rgba"].astype(np.int16)).max() <= parity.RGB_TOL, kname
+        assert np.array_equal(rgba, g["rgba"]), kname
+        leaf = (flags & K.FLAG_LEAF) > 0
+        assert np.array_equal(g["model_s"][leaf], aux[leaf][:, K.AUX_MODEL_S]), kname
+        assert np.array_equal(g["model_d"][leaf], aux[leaf][:, K.AUX_MODEL_D]), kname
+        shaded = (flags & K.FLAG_SHADED) > 0
+        assert np.array_equal(g["shadow"][shaded] != 0, (flags[shaded] & K.FLAG_LIT) > 0), kname
     rc.destroy()
