@@ -29,6 +29,7 @@ sys.path.insert(0, ROOT)
 WIDTH, HEIGHT = 1920, 1080
 MAXLEVEL, BASESIZE = 12, 1800.0
 TILE = 64
+DIVISION = 0
 METRIC = "Mrays/s (primary+shadow) at 1080p, 90M-pt octree"
 UNIT = "Mrays/s"
 
@@ -154,7 +155,7 @@ def cpu_port_sample(sc, pose, rows, threads):
     osc = O.OracleScene(sc)
     u = O.uniforms(WIDTH, HEIGHT, pose[0], pose[1], maxlevel=MAXLEVEL, basesize=BASESIZE)
     t = time.time()
-    r = O.render(osc, u, rows=rows, threads=threads, want_aux=False)
+    r = O.render(osc, u, rows=rows, threads=threads, want_aux=False, div=DIVISION)
     dt = time.time() - t
     c = r["counters"]
     rays = c["rays_primary"] + c["rays_shadow"] + c["rays_disc"]
@@ -283,6 +284,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="1.0 = the full 90M-point level")
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic, 2 fast")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"])
+    ap.add_argument("--division", type=int, default=0, help="0 GLSL a*(1/b) (reference shader on llvmpipe), 1 IEEE")
     ap.add_argument("--cpu-rows", type=int, default=24, help="rows of the frame the cpu_baseline sample renders")
     ap.add_argument("--ref-pixels", type=int, default=65536)
     ap.add_argument("--cpu-passes", type=int, default=2)
@@ -290,6 +292,8 @@ def main():
     ap.add_argument("--no-flush", action="store_true")
     args = ap.parse_args()
 
+    global DIVISION
+    DIVISION = args.division
     if args.impl == "reference":
         return reference_arm(args)
 
@@ -323,35 +327,16 @@ def main():
     rc.sync()
     log("rank %d: scene uploaded in %.1f s, device memory %.2f GB" % (rank, time.time() - t0, rc.memsize / 1e9))
     rc.set_kernel(args.kernel)
-    rc.set_shard(rank, world, TILE, TILE)
+    rc.set_division(args.division)
 
     def render(i):
         pos, ang = poses[i % len(poses)]
         rc.update(WIDTH, HEIGHT, pos, ang, 0.0, 10, MAXLEVEL, BASESIZE, 0)
 
-    # frame assembly for N > 1
-    peer_ptr = 0
-    fence = torch.zeros(1, device=dev)
-    if world > 1:
-        rc.reserve_frame(WIDTH, HEIGHT, 1)
-        if args.gather == "p2p":
-            h = torch.from_numpy(rc.ipc_export_frame().copy()).to(dev) if rank == 0 else torch.zeros(
-                64, dtype=torch.uint8, device=dev)
-            dist.broadcast(h, 0)
-            if rank != 0:
-                peer_ptr = rc.ipc_open(h.cpu().numpy())
-                rc.set_frame_target(peer_ptr, WIDTH)
-        else:
-            frame_t = torch.zeros((HEIGHT, WIDTH), dtype=torch.int32, device=dev)
-            rc.set_frame_target(frame_t.data_ptr(), WIDTH, keepalive=frame_t)
-
-    def assemble():
-        if world == 1:
-            return
-        if args.gather == "p2p":
-            dist.all_reduce(fence)  # all peer stores of this frame are complete after this
-        else:
-            dist.reduce(frame_t, 0, op=dist.ReduceOp.SUM)  # disjoint tiles, zeros elsewhere
+    # frame assembly for N > 1 (qubatron_b200/multigpu.py): peer stores into rank 0's framebuffer, or NCCL reduce
+    from qubatron_b200 import multigpu
+    sharded = multigpu.ShardedFrame(rc, WIDTH, HEIGHT, rank, world, dev, gather=args.gather, tile=TILE)
+    assemble = sharded.assemble
 
     # ---- per-pose work counters (counting instantiation, outside the timed region) ----
     rc.enable_counters(True)
@@ -466,10 +451,7 @@ def main():
             render(i)
             assemble()
             if rank == 0:
-                if args.gather == "p2p":
-                    rc.read_frame(host_frame)
-                else:
-                    host_frame[...] = frame_t.cpu().numpy().view(np.uint8).reshape(HEIGHT, WIDTH, 4)
+                sharded.read_frame(host_frame)
         torch.cuda.synchronize()
         barrier()
         e2e_s = time.time() - t
@@ -504,6 +486,8 @@ def main():
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "wall_s_timed_region": wall, "kernel": {1: "generic", 2: "fast"}.get(kernel_used),
             "gather": args.gather if world > 1 else None,
+            "division": {0: "glsl a*(1/b) (matches the reference shader on llvmpipe bit for bit)",
+                         1: "ieee a/b (matches the reference CPU twin)"}[args.division],
         }
         if not args.no_cpu and world == 1:
             cores = os.cpu_count() or 1
@@ -519,8 +503,7 @@ def main():
                                              "%.1f s of CPU wall time" % (args.cpu_passes, len(poses), dt)}
         print(json.dumps(out), flush=True)
 
-    if peer_ptr:
-        rc.ipc_close(peer_ptr)
+    sharded.close()
     barrier()
     rc.destroy()
     if world > 1:

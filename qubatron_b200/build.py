@@ -8,7 +8,8 @@ HOST_CC = "/usr/bin/gcc"
 
 def lib_paths():
     return {
-        "cuc": os.path.join(_HERE, "liboctree_cuc.so"),
+        # QB_CUC_LIB: developer override to A/B-test a differently tuned build of the same sources
+        "cuc": os.environ.get("QB_CUC_LIB") or os.path.join(_HERE, "liboctree_cuc.so"),
         "host": os.path.join(_HERE, "libqb_host.so"),
     }
 

@@ -1,0 +1,152 @@
+"""Image-tile sharding of one frame over the GPUs of a box (one process per GPU, torch.distributed).
+
+The path shards by pixels: the octree and the point arrays are replicated, every rank renders the tiles whose
+row-major index is congruent to its rank modulo the world size (interleaving averages out sky-vs-geometry
+imbalance), and the only per-frame exchange is the assembly of the tiles:
+
+  gather="p2p"   rank 0 exports its framebuffer as a CUDA IPC handle; the other ranks map it and their render
+                 kernels store their pixels straight into it over NVLink (peer stores), so the transfer overlaps
+                 the traversal; one tiny all-reduce per frame is the completion fence.
+  gather="nccl"  every rank renders into a zero-initialised full-size buffer of its own and the frame is the
+                 NCCL reduce(SUM) of the buffers viewed as int32 (tiles are disjoint, so the sum is the union).
+
+Range updates ("zero-and-append", modelutil.c L429-501) are received by rank 0 through the reference API, exported
+as one packed blob (octree_cuc_export_pending), broadcast, and applied by every rank (octree_cuc_apply_blob).
+
+The tile ownership rule and the blob format are plain host logic, kept here so that CPU (gloo) tests cover them.
+"""
+import numpy as np
+
+BLOCK_W, BLOCK_H = 16, 8  # CTA footprint of the render kernels (octree_types.cuh)
+
+
+def tile_grid(width, height, tile_w, tile_h):
+    return (width + tile_w - 1) // tile_w, (height + tile_h - 1) // tile_h
+
+
+def tile_owner_map(width, height, world, tile_w=64, tile_h=64):
+    """int32 [H,W]: rank that renders each pixel (same rule as render kernels: tile index % world)."""
+    if tile_w % BLOCK_W or tile_h % BLOCK_H:
+        raise ValueError("tile size must be a multiple of %dx%d" % (BLOCK_W, BLOCK_H))
+    tx, _ = tile_grid(width, height, tile_w, tile_h)
+    ys = np.arange(height)[:, None] // tile_h
+    xs = np.arange(width)[None, :] // tile_w
+    return ((ys * tx + xs) % world).astype(np.int32)
+
+
+def tiles_of_rank(width, height, rank, world, tile_w=64, tile_h=64):
+    tx, ty = tile_grid(width, height, tile_w, tile_h)
+    return list(range(rank, tx * ty, world))
+
+
+# ---- range-update blob: { uint64 ndesc, uint64 payload_bytes, desc[ndesc], payload } ---------------------------
+DESC_DTYPE = np.dtype([("dst_word", "<u8"), ("src_word", "<u4"), ("nwords", "<u4"), ("buftype", "<i4"), ("pad", "<i4")])
+
+
+def pack_ranges(ranges):
+    """ranges: list of (buftype, start_byte, data_bytes ndarray uint8 with len % 4 == 0) -> blob (uint8 array).
+    Same layout octree_cuc_export_pending produces, so host code can also build blobs directly."""
+    descs = np.zeros(len(ranges), dtype=DESC_DTYPE)
+    payload = []
+    used = 0
+    for i, (buftype, start, data) in enumerate(ranges):
+        data = np.ascontiguousarray(data).view(np.uint8).ravel()
+        if start % 4 or data.size % 4:
+            raise ValueError("ranges are 4-byte granular")
+        descs[i] = (start // 4, used // 4, data.size // 4, buftype, 0)
+        payload.append(data)
+        used += data.size
+    hdr = np.array([len(ranges), used], dtype="<u8")
+    parts = [hdr.view(np.uint8), descs.view(np.uint8)] + payload
+    return np.concatenate(parts) if parts else np.zeros(16, np.uint8)
+
+
+def unpack_ranges(blob):
+    blob = np.ascontiguousarray(blob, dtype=np.uint8)
+    nd, nbytes = [int(v) for v in blob[:16].view("<u8")]
+    descs = blob[16:16 + nd * DESC_DTYPE.itemsize].view(DESC_DTYPE)
+    payload = blob[16 + nd * DESC_DTYPE.itemsize:]
+    assert payload.size == nbytes
+    out = []
+    for d in descs:
+        s, n = int(d["src_word"]) * 4, int(d["nwords"]) * 4
+        out.append((int(d["buftype"]), int(d["dst_word"]) * 4, payload[s:s + n].copy()))
+    return out
+
+
+def broadcast_blob(blob, src=0, device=None):
+    """Broadcast a variable-size blob from `src` with torch.distributed (NCCL on GPUs, gloo in CPU tests)."""
+    import torch
+    import torch.distributed as dist
+    rank = dist.get_rank()
+    size = torch.tensor([len(blob) if rank == src else 0], dtype=torch.int64, device=device)
+    dist.broadcast(size, src)
+    buf = torch.empty(int(size.item()), dtype=torch.uint8, device=device)
+    if rank == src:
+        buf.copy_(torch.from_numpy(np.ascontiguousarray(blob, dtype=np.uint8)))
+    dist.broadcast(buf, src)
+    return buf.cpu().numpy()
+
+
+class ShardedFrame:
+    """Frame assembly for N ranks around one OctreeGlc per rank (used by bench.py and the multi-GPU tests)."""
+
+    def __init__(self, rc, width, height, rank, world, device, gather="p2p", tile=64):
+        import torch
+        import torch.distributed as dist
+        self.rc, self.rank, self.world, self.gather = rc, rank, world, gather
+        self.width, self.height = width, height
+        self.dist, self.torch = dist, torch
+        self.peer_ptr = 0
+        self.frame_t = None
+        self.fence = torch.zeros(1, device=device)
+        rc.set_shard(rank, world, tile, tile)
+        if world == 1:
+            return
+        rc.reserve_frame(width, height, 1)
+        if gather == "p2p":
+            h = torch.from_numpy(rc.ipc_export_frame().copy()).to(device) if rank == 0 else torch.zeros(
+                64, dtype=torch.uint8, device=device)
+            dist.broadcast(h, 0)
+            if rank != 0:
+                self.peer_ptr = rc.ipc_open(h.cpu().numpy())
+                rc.set_frame_target(self.peer_ptr, width)
+        elif gather == "nccl":
+            self.frame_t = torch.zeros((height, width), dtype=torch.int32, device=device)
+            rc.set_frame_target(self.frame_t.data_ptr(), width, keepalive=self.frame_t)
+        else:
+            raise ValueError(gather)
+
+    def assemble(self):
+        """Queue the per-frame exchange on the current stream (after the rank's render)."""
+        if self.world == 1:
+            return
+        if self.gather == "p2p":
+            self.dist.all_reduce(self.fence)  # every rank's peer stores for this frame are complete after this
+        else:
+            self.dist.reduce(self.frame_t, 0, op=self.dist.ReduceOp.SUM)  # disjoint tiles, zeros elsewhere
+
+    def read_frame(self, out=None):
+        """Rank 0: the assembled RGBA8 frame as uint8 [H,W,4] (synchronises)."""
+        if self.world == 1 or self.gather == "p2p":
+            return self.rc.read_frame(out)
+        host = self.frame_t.cpu().numpy().view(np.uint8).reshape(self.height, self.width, 4)
+        if out is not None:
+            out[...] = host
+            return out
+        return host
+
+    def broadcast_updates(self, device):
+        """Rank 0's pending range uploads -> every rank (rank 0 applies its own at the next frame)."""
+        if self.world == 1:
+            return 0
+        blob = self.rc.export_pending() if self.rank == 0 else None
+        blob = broadcast_blob(blob, 0, device)
+        if self.rank != 0:
+            self.rc.apply_blob(blob)
+        return len(blob)
+
+    def close(self):
+        if self.peer_ptr:
+            self.rc.ipc_close(self.peer_ptr)
+            self.peer_ptr = 0

@@ -1,0 +1,92 @@
+"""Worker of the multi-GPU parity test (launched by torchrun, one rank per GPU, NCCL).
+
+Checks, against the CPU oracle on rank 0:
+  * tile-sharded frame assembled by peer stores over NVLink (gather="p2p") and by NCCL reduce (gather="nccl");
+  * range updates received by rank 0 through the reference API, broadcast as a blob and applied on every rank.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import parity  # noqa: E402
+from oracle import qb_oracle as O  # noqa: E402
+from qubatron_b200 import connector as K, multigpu, scene as S  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+
+    sc = S.make_random(30000, 4000, seed=11)
+    W, H = 300, 170
+    pos, ang = (760.0, 200.0, 420.0), (-0.05, -0.12, 0.0)
+    ok = True
+    for gather in ("p2p", "nccl"):
+        rc = K.OctreeGlc(b"", device=local)
+        rc.set_stream(stream.cuda_stream)
+        rc.upload_scene(sc)
+        sh = multigpu.ShardedFrame(rc, W, H, rank, world, dev, gather=gather, tile=32)
+        for it in range(3):
+            rc.update(W, H, pos, ang, shoot=it & 1)
+            sh.assemble()
+        torch.cuda.synchronize()
+        dist.barrier()
+        if rank == 0:
+            got = sh.read_frame()
+            ref = O.render(O.OracleScene(sc), O.uniforms(W, H, pos, ang, shoot=0))
+            d = int(np.abs(got.astype(np.int16) - ref["rgba"].astype(np.int16)).max())
+            print("gather=%s world=%d max rgba diff %d" % (gather, world, d), flush=True)
+            ok = ok and d <= parity.RGB_TOL
+
+        # zero-and-append on rank 0 only, then broadcast
+        tree = S.HostOctree()
+        tree.insert_points(sc.pnt_s)
+        col = sc.col_s.copy()
+        if rank == 0:
+            centre = sc.pnt_s[np.argmin(np.linalg.norm(sc.pnt_s - np.array([810.0, 180.0, 270.0], np.float32), axis=1))]
+            near = np.nonzero(np.linalg.norm(sc.pnt_s - centre[None, :], axis=1) < 25.0)[0][:300]
+            for v in near:
+                m, o = tree.remove_point(sc.pnt_s[v])
+                if o >= 0:
+                    nodes = tree.nodes(copy=False)
+                    rc.upload_texbuffer_data(nodes, K.GL_INT, len(nodes) * 48, 16, o * 48, (o + 1) * 48,
+                                             K.STATIC_OCTREE)
+                    col[m] = (1.0, 0.0, 1.0)
+            lo, hi = int(near.min()), int(near.max()) + 1
+            rc.upload_points(col, K.STATIC_COLOR, lo, hi)
+        nbytes = sh.broadcast_updates(dev)
+        rc.update(W, H, pos, ang)
+        sh.assemble()
+        torch.cuda.synchronize()
+        dist.barrier()
+        if rank == 0:
+            final = S.Scene("upd", sc.pnt_s, col, sc.nrm_s, tree.nodes(), sc.pnt_d, sc.col_d, sc.nrm_d, sc.oct_d)
+            ref2 = O.render(O.OracleScene(final), O.uniforms(W, H, pos, ang))
+            got2 = sh.read_frame()
+            d2 = int(np.abs(got2.astype(np.int16) - ref2["rgba"].astype(np.int16)).max())
+            changed = int((ref2["rgba"] != ref["rgba"]).any(axis=-1).sum())
+            print("gather=%s after broadcast of %d blob bytes: max rgba diff %d, %d pixels changed by the edit"
+                  % (gather, nbytes, d2, changed), flush=True)
+            ok = ok and d2 <= parity.RGB_TOL and changed > 0
+        sh.close()
+        dist.barrier()
+        rc.destroy()
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.broadcast(flag, 0)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

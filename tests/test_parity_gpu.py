@@ -351,3 +351,17 @@ def test_golden_frames_of_the_reference_shader(name):
         shaded = (flags & K.FLAG_SHADED) > 0
         assert np.array_equal(g["shadow"][shaded] != 0, (flags[shaded] & K.FLAG_LIT) > 0), kname
     rc.destroy()
+
+
+def test_c_host_demo():
+    """examples/host_demo.c: a plain-C host making the reference engine's own call sequence against the library."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ex = os.path.join(root, "examples")
+    r = subprocess.run(["make", "-C", ex], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    r = subprocess.run([os.path.join(ex, "host_demo")], cwd=ex, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       text=True, timeout=120)
+    assert r.returncode == 0, r.stdout
+    assert "leaf pixels" in r.stdout
