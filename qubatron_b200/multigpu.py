@@ -99,6 +99,7 @@ class ShardedFrame:
         self.dist, self.torch = dist, torch
         self.peer_ptr = 0
         self.frame_t = None
+        self.out_t = None
         self.fence = torch.zeros(1, device=device)
         rc.set_shard(rank, world, tile, tile)
         if world == 1:
@@ -113,6 +114,9 @@ class ShardedFrame:
                 rc.set_frame_target(self.peer_ptr, width)
         elif gather == "nccl":
             self.frame_t = torch.zeros((height, width), dtype=torch.int32, device=device)
+            # rank 0 reduces into a second buffer: an in-place reduce would leave the other ranks' tiles in
+            # its render target and add them again on the next frame
+            self.out_t = torch.zeros_like(self.frame_t) if rank == 0 else None
             rc.set_frame_target(self.frame_t.data_ptr(), width, keepalive=self.frame_t)
         else:
             raise ValueError(gather)
@@ -124,13 +128,17 @@ class ShardedFrame:
         if self.gather == "p2p":
             self.dist.all_reduce(self.fence)  # every rank's peer stores for this frame are complete after this
         else:
-            self.dist.reduce(self.frame_t, 0, op=self.dist.ReduceOp.SUM)  # disjoint tiles, zeros elsewhere
+            if self.rank == 0:
+                self.out_t.copy_(self.frame_t)
+                self.dist.reduce(self.out_t, 0, op=self.dist.ReduceOp.SUM)  # disjoint tiles, zeros elsewhere
+            else:
+                self.dist.reduce(self.frame_t, 0, op=self.dist.ReduceOp.SUM)
 
     def read_frame(self, out=None):
         """Rank 0: the assembled RGBA8 frame as uint8 [H,W,4] (synchronises)."""
         if self.world == 1 or self.gather == "p2p":
             return self.rc.read_frame(out)
-        host = self.frame_t.cpu().numpy().view(np.uint8).reshape(self.height, self.width, 4)
+        host = self.out_t.cpu().numpy().view(np.uint8).reshape(self.height, self.width, 4)
         if out is not None:
             out[...] = host
             return out

@@ -1,0 +1,51 @@
+"""Turn an ncu report into the committed summaries under profiles/:
+   python scripts/ncu_profile_summary.py gpurun_out/prof.ncu-rep profiles/r1_<tag> [--traffic]
+writes <out>_raw_summary.json (+ profiles/traffic.json with --traffic) and <out>_source_summary.txt"""
+import csv
+import io
+import json
+import subprocess
+import sys
+
+rep, out = sys.argv[1], sys.argv[2]
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
+rows = list(csv.reader(io.StringIO(raw)))
+hdr, units, data = rows[0], rows[1], rows[2:]
+idx = {h: i for i, h in enumerate(hdr)}
+keys = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
+        "smsp__thread_inst_executed_per_inst_executed.ratio", "launch__registers_per_thread",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "launch__grid_size", "launch__block_size", "smsp__warps_eligible.avg.per_cycle_active",
+        "sm__cycles_elapsed.avg", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "launch__shared_mem_per_block_dynamic"]
+launches = [{"launch": i, **{k: (r[idx[k]] + " " + units[idx[k]]).strip() for k in keys if k in idx}}
+            for i, r in enumerate(data)]
+json.dump({"what": "ncu --set full --clock-control none; bench workload C2 at full scale, one launch per camera "
+                   "pose (0 start pose, 1 inside building, 2 open sky, 3 grazing terrain); ncu flushes caches "
+                   "between replays, so DRAM figures are cold-cache", "report": rep, "launches": launches},
+          open(out + "_raw_summary.json", "w"), indent=1)
+
+
+def num(r, k):
+    return float(r[idx[k]])
+
+
+def to_bytes(v, unit):
+    return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+
+
+if "--traffic" in sys.argv:
+    tot = [to_bytes(num(r, "dram__bytes_read.sum"), units[idx["dram__bytes_read.sum"]])
+           + to_bytes(num(r, "dram__bytes_write.sum"), units[idx["dram__bytes_write.sum"]]) for r in data]
+    json.dump({"dram_bytes_per_launch": sum(tot) / len(tot), "per_pose": tot, "source": out + "_raw_summary.json",
+               "note": "dram__bytes_read.sum + dram__bytes_write.sum of the render kernel, mean over the four poses"},
+              open("profiles/traffic.json", "w"), indent=1)
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:render", "--launch-skip",
+                      "0", "--launch-count", "1"], stdout=subprocess.PIPE, text=True).stdout
+open("/tmp/_src.csv", "w").write(src)
+txt = subprocess.run([sys.executable, "scripts/ncu_source_summary.py", "/tmp/_src.csv", "12"], stdout=subprocess.PIPE,
+                     text=True).stdout
+open(out + "_source_summary.txt", "w").write(txt)
+print(json.dumps(launches[0], indent=1))
