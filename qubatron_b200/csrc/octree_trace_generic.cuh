@@ -90,6 +90,47 @@ __device__ __forceinline__ float4 plane_hit_z(float c, float3 o, float3 d)
     return r;
 }
 
+// the same three with the quotient supplied by the caller (per-ray reciprocals hoisted)
+template <class Q>
+__device__ __forceinline__ float4 plane_hit_x_q(float c, float3 o, float3 d, Q q)
+{
+    float4 r = make_float4(FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX);
+    if (d.x != 0.0f)
+    {
+        r.w = q(c - o.x, 0);
+        r.y = o.y + d.y * r.w;
+        r.z = o.z + d.z * r.w;
+        r.x = c;
+    }
+    return r;
+}
+template <class Q>
+__device__ __forceinline__ float4 plane_hit_y_q(float c, float3 o, float3 d, Q q)
+{
+    float4 r = make_float4(FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX);
+    if (d.y != 0.0f)
+    {
+        r.w = q(c - o.y, 1);
+        r.x = o.x + d.x * r.w;
+        r.z = o.z + d.z * r.w;
+        r.y = c;
+    }
+    return r;
+}
+template <class Q>
+__device__ __forceinline__ float4 plane_hit_z_q(float c, float3 o, float3 d, Q q)
+{
+    float4 r = make_float4(FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX);
+    if (d.z != 0.0f)
+    {
+        r.w = q(c - o.z, 2);
+        r.x = o.x + d.x * r.w;
+        r.y = o.y + d.y * r.w;
+        r.z = c;
+    }
+    return r;
+}
+
 // half-open cube ranges: x in (x0, x1], y in [y0, y1), z in [z0, z1)
 struct Cube
 {
@@ -138,6 +179,45 @@ __device__ __forceinline__ int model_of(const TreeDev& t, int node, int level)
 }
 
 // base-cube entry (octree_fsh.c L157-211).  Returns false on `discard`.
+// q(n, axis) returns n / dir[axis] in the caller's division semantics.
+template <class Q>
+__device__ __forceinline__ bool base_cube_entry_q(const float* basecube, float3 pos, float3 dir, float4& entry, Q q)
+{
+    Cube c;
+    c.x0 = basecube[0];
+    c.x1 = basecube[0] + basecube[3];
+    c.y1 = basecube[1];
+    c.y0 = basecube[1] - basecube[3];
+    c.z1 = basecube[2];
+    c.z0 = basecube[2] - basecube[3];
+
+    int    hitc = 0;
+    float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f), h1 = h0, act;
+
+#define QB_FACE(ACT, COND)                                                                                            \
+    act = ACT;                                                                                                        \
+    if (COND)                                                                                                         \
+    {                                                                                                                 \
+        if (hitc == 0) h0 = act;                                                                                      \
+        if (hitc == 1) h1 = act;                                                                                      \
+        hitc++;                                                                                                       \
+    }
+    QB_FACE(plane_hit_z_q(c.z1, pos, dir, q), in_x(c, act.x) && in_y(c, act.y)) // front
+    QB_FACE(plane_hit_z_q(c.z0, pos, dir, q), in_x(c, act.x) && in_y(c, act.y)) // back
+    QB_FACE(plane_hit_x_q(c.x0, pos, dir, q), in_y(c, act.y) && in_z(c, act.z)) // left
+    QB_FACE(plane_hit_x_q(c.x1, pos, dir, q), in_y(c, act.y) && in_z(c, act.z)) // right
+    QB_FACE(plane_hit_y_q(c.y1, pos, dir, q), in_x(c, act.x) && in_z(c, act.z)) // top
+    QB_FACE(plane_hit_y_q(c.y0, pos, dir, q), in_x(c, act.x) && in_z(c, act.z)) // bottom
+#undef QB_FACE
+
+    if (hitc < 2) return false;                   // L195
+    if (h0.w < 0.0f && h1.w < 0.0f) return false; // L198
+    if (h1.w < h0.w) h0 = h1;                     // L205
+    if (h0.w < 0.0f) h0 = make_float4(pos.x, pos.y, pos.z, 0.0f); // L208
+    entry = h0;
+    return true;
+}
+
 template <int DIV>
 __device__ __forceinline__ bool base_cube_entry(const float* basecube, float3 pos, float3 dir, float4& entry)
 {
