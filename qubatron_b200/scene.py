@@ -420,3 +420,16 @@ def make_random(n_static=20000, n_dynamic=3000, seed=7, levels=LEVELS, basesize=
     d = cloud(n_dynamic, np.array([basesize * 0.44, basesize * 0.11, basesize * 0.16]), basesize * 0.012) \
         if n_dynamic else None
     return build_scene("random_%d_%d" % (n_static, n_dynamic), s, d, basesize=basesize, levels=levels)
+
+
+def octant_paths(points, basesize=BASESIZE, levels=LEVELS):
+    """The 12 octant digits of every point (what skeleton_vsh.c L188-226 emits per skinned point and
+    octree_insert_path consumes, qubatron.c L439-452): same arithmetic as octree_insert_point (octree.c L102-109)."""
+    p = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 3)
+    out = np.zeros((len(p), 12), dtype=np.int32)
+    size = np.float32(basesize)
+    for level in range(levels):
+        size = np.float32(size / np.float32(2.0))
+        q = (p / size).astype(np.int32) % 2
+        out[:, level] = q[:, 0] + np.where(q[:, 1] == 0, 2, 0) + np.where(q[:, 2] == 0, 4, 0)
+    return out

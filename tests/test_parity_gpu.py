@@ -365,3 +365,36 @@ def test_c_host_demo():
                        text=True, timeout=120)
     assert r.returncode == 0, r.stdout
     assert "leaf pixels" in r.stdout
+
+
+def test_dynamic_tree_rebuilt_every_frame(scene_c1):
+    """BASELINE config 4 at test size: per frame the dynamic tree is reset and rebuilt from re-pathed points
+    (octree_reset + octree_insert_path, qubatron.c L439-452), uploaded whole (L508-516) together with the normals
+    [0, n) from a DIFFERENT host buffer (L521-529), then the frame is rendered."""
+    rng = np.random.default_rng(12)
+    fig_p, fig_c, fig_n = S.zombie_raw(base=(760.0, 100.0, 230.0), spacing=0.6, shells=2)
+    fig_p, fig_cf, fig_n = S.voxelise(fig_p, fig_c, fig_n)
+    n = len(fig_p)
+    rc = K.OctreeGlc(b"", device=0)
+    rc.upload_points(scene_c1.col_s, K.STATIC_COLOR)
+    rc.upload_points(scene_c1.nrm_s, K.STATIC_NORMAL)
+    rc.upload_octree(scene_c1.oct_s)
+    rc.upload_points(fig_cf, K.DYNAMIC_COLOR)
+    rc.enable_aux(True)
+    tree = S.HostOctree()
+    W, H = 320, 180
+    seen_dynamic = 0
+    for frame in range(3):
+        moved = (fig_p + np.array([3.0 * frame, 0.0, -2.0 * frame], np.float32)).astype(np.float32)
+        nrm_out = (fig_n + rng.normal(0, 0.05, size=fig_n.shape)).astype(np.float32)  # skelglc.nrm_out analogue
+        tree.reset()
+        tree.insert_paths(S.octant_paths(moved))
+        nodes = tree.nodes()
+        rc.upload_texbuffer_data(nodes, K.GL_INT, len(nodes) * 48, 16, 0, len(nodes) * 48, K.DYNAMIC_OCTREE)
+        rc.upload_texbuffer_data(nrm_out, K.GL_FLOAT, n * 12, 12, 0, n * 12, K.DYNAMIC_NORMAL)
+        sc = S.Scene("dyn", scene_c1.pnt_s, scene_c1.col_s, scene_c1.nrm_s, scene_c1.oct_s, moved, fig_cf, nrm_out,
+                     nodes)
+        ref, _ = _render_and_compare(sc, W, H, *S.CAMERA_C1, rc=rc, lighta=0.3 * frame)
+        seen_dynamic += int((ref["aux"][..., K.AUX_MODEL_D] > 0).sum())
+    assert seen_dynamic > 3000
+    rc.destroy()
