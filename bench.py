@@ -266,7 +266,7 @@ def bench_config(meta, args, world):
                         % (meta["name"], meta["static_points"], meta["static_nodes"], meta["dynamic_points"],
                            meta["dynamic_nodes"], MAXLEVEL, BASESIZE, WIDTH, HEIGHT, len(meta["cameras"])),
             "scale": args.scale, "width": WIDTH, "height": HEIGHT, "maxlevel": MAXLEVEL,
-            "parallelism": "image tiles %dx%d interleaved over %d GPU(s), octree replicated" % (TILE, TILE, world),
+            "parallelism": "image tiles %dx%d interleaved over %d GPU(s), octree replicated" % (args.tile, args.tile, world),
             "l2": "flushed before every step (256 MiB memset, outside the step's event pair); scene arrays "
                   "(%.1f GB) also exceed L2" % ((meta["static_nodes"] + meta["dynamic_nodes"]) * 36e-9
                                                 + (meta["static_points"] + meta["dynamic_points"]) * 32e-9)}
@@ -287,7 +287,8 @@ def main():
     ap.add_argument("--division", type=int, default=0, help="0 GLSL a*(1/b) (reference shader on llvmpipe), 1 IEEE")
     ap.add_argument("--cpu-rows", type=int, default=24, help="rows of the frame the cpu_baseline sample renders")
     ap.add_argument("--ref-pixels", type=int, default=65536)
-    ap.add_argument("--cpu-passes", type=int, default=2)
+    ap.add_argument("--cpu-passes", type=int, default=10)
+    ap.add_argument("--tile", type=int, default=64, help="shard tile edge in pixels (multiple of 16)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
     args = ap.parse_args()
@@ -335,7 +336,7 @@ def main():
 
     # frame assembly for N > 1 (qubatron_b200/multigpu.py): peer stores into rank 0's framebuffer, or NCCL reduce
     from qubatron_b200 import multigpu
-    sharded = multigpu.ShardedFrame(rc, WIDTH, HEIGHT, rank, world, dev, gather=args.gather, tile=TILE)
+    sharded = multigpu.ShardedFrame(rc, WIDTH, HEIGHT, rank, world, dev, gather=args.gather, tile=args.tile)
     assemble = sharded.assemble
 
     # ---- per-pose work counters (counting instantiation, outside the timed region) ----
