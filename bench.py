@@ -257,7 +257,7 @@ def reference_arm(args):
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out), flush=True)
+    emit(json.dumps(out))
 
 
 def bench_config(meta, args, world):
@@ -275,7 +275,44 @@ def bench_config(meta, args, world):
 # ---------------------------------------------------------------------------
 # main arm
 # ---------------------------------------------------------------------------
+class _CleanStdout:
+    """Libraries (NCCL's version banner, for one) write to stdout; the contract is ONE JSON line there.
+    Everything printed while this is active goes to stderr, the JSON line is written to the real stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.write(self.real, (line + "\n").encode())
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.real, 1)
+        os.close(self.real)
+
+
+OUT = None
+
+
+def emit(line):
+    if OUT is not None:
+        OUT.emit(line)
+    else:
+        print(line, flush=True)
+
+
 def main():
+    global OUT
+    with _CleanStdout() as OUT:
+        _main()
+    OUT = None
+
+
+def _main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
@@ -502,7 +539,7 @@ def main():
                                    "sample": "oracle restatement of octree_fsh (both trees, shading): %d pass(es) over "
                                              "the full 1080p frame of each of the %d poses, OpenMP over rows, "
                                              "%.1f s of CPU wall time" % (args.cpu_passes, len(poses), dt)}
-        print(json.dumps(out), flush=True)
+        emit(json.dumps(out))
 
     sharded.close()
     barrier()

@@ -619,6 +619,10 @@ static void counters_add(qb_counters* dst, const qb_counters* src)
     dst->descents += src->descents;
 }
 
+/* optional per-pixel work plane (descents of all rays of the pixel), for load-balance studies */
+static int32_t* g_work_plane = NULL;
+void            qb_oracle_set_work_plane(int32_t* plane) { g_work_plane = plane; }
+
 void qb_oracle_render(const qb_scene* sc, const qb_uniforms* u, int row0, int row1, uint8_t* rgba, uint8_t* flags,
                       int32_t* aux, qb_counters* counters, int threads)
 {
@@ -644,9 +648,11 @@ void qb_oracle_render(const qb_scene* sc, const qb_uniforms* u, int row0, int ro
         {
             for (int px = 0; px < W; px++)
             {
-                int64_t p = (int64_t) py * W + px;
+                int64_t p  = (int64_t) py * W + px;
+                int64_t d0 = local.descents;
                 shade_pixel(sc, u, &fc, px, py, rgba + p * 4, flags ? flags + p : NULL,
-                            aux ? aux + p * QB_AUX_STRIDE : NULL, counters ? &local : NULL);
+                            aux ? aux + p * QB_AUX_STRIDE : NULL, (counters || g_work_plane) ? &local : NULL);
+                if (g_work_plane) g_work_plane[p] = (int32_t) (local.descents - d0);
             }
         }
 #pragma omp critical
