@@ -250,7 +250,10 @@ def reference_arm(args):
         step_s.append(s)
     total_s = float(np.sum(step_s))
     value = float(np.sum(step_rays)) / total_s / 1e6
-    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+    extras = {}
+    if not args.no_c1:
+        extras["c1_640x360_reference_shader_on_llvmpipe"] = c1_llvmpipe()
+    out = {"impl": "reference", "extras": extras, "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_s / args.steps,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": bench_config(meta, args, 1),
@@ -258,6 +261,79 @@ def reference_arm(args):
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     emit(json.dumps(out))
+
+
+def c1_llvmpipe():
+    """BASELINE configs[0]: the reference's UNMODIFIED shader on Mesa llvmpipe (oracle/_ref/glsl_ref), 1 M-point
+    cloud, one 640x360 primary+shadow frame; steady-state frame time with all host threads and with one."""
+    from oracle import qb_oracle as O
+    from qubatron_b200 import scene as S
+    if not O.have_glsl():
+        return {"unavailable": "oracle/_ref/glsl_ref or the bundled Mesa libGL is missing on this box"}
+    try:
+        sc = S.make_c1()
+        u = O.uniforms(640, 360, *S.CAMERA_C1)
+        c = O.render(O.OracleScene(sc), u, want_aux=False)["counters"]
+        rays = c["rays_primary"] + c["rays_shadow"] + c["rays_disc"]
+        _, info = O.glsl_render(sc, u, repeat=6)
+        steady = float(np.median(info["frame_s"][1:]))
+        _, info1 = O.glsl_render(sc, u, repeat=2, threads=1)
+        return {"renderer": info["renderer"], "rays_per_frame": rays, "first_frame_s": info["frame_s"][0],
+                "frame_s": steady, "mrays_s": rays / steady / 1e6, "threads": "LP_NUM_THREADS default (= cores, max 16)",
+                "frame_s_1_thread": info1["frame_s"][-1], "mrays_s_1_thread": rays / info1["frame_s"][-1] / 1e6,
+                "cores": os.cpu_count()}
+    except Exception as e:  # the baseline is reported, never fatal
+        return {"unavailable": repr(e)[:300]}
+
+
+def c1_gpu(K, device):
+    """The same configs[0] frame on the GPU through the C ABI (device time per frame)."""
+    from oracle import qb_oracle as O
+    from qubatron_b200 import scene as S
+    sc = S.make_c1()
+    rc = K.OctreeGlc(b"", device=device)
+    rc.upload_scene(sc)
+    rc.enable_counters(True)
+    rc.update(640, 360, *S.CAMERA_C1)
+    c = rc.read_counters()
+    rc.enable_counters(False)
+    ms = []
+    for _ in range(24):
+        rc.update(640, 360, *S.CAMERA_C1)
+        ms.append(rc.last_frame_ms())
+    rc.destroy()
+    rays = c["rays_primary"] + c["rays_shadow"] + c["rays_disc"]
+    m = float(np.median(ms[4:]))
+    return {"rays_per_frame": rays, "frame_ms": m, "mrays_s": rays / m / 1e3,
+            "note": "1 M-point cloud, 640x360, octree (28 MB) is L2-resident; kernel time, CUDA events"}
+
+
+def c5_views(rc, sc, rank, world, dev, dist, torch):
+    """BASELINE configs[4]: 64 views with random (incoherent) cameras on the same level, whole views sharded
+    across the ranks (no exchange at all), one octree_cuc_update_views launch per rank."""
+    rng = np.random.default_rng(777)
+    n = 64
+    pos = np.stack([rng.uniform(150, 1650, n), rng.uniform(90, 330, n), rng.uniform(150, 1650, n)], axis=1)
+    ang = np.stack([rng.uniform(0, 2 * np.pi, n), rng.uniform(-0.6, 0.6, n), np.zeros(n)], axis=1)
+    mine = list(range(rank, n, world))
+    rc.set_frame_target(0, 0)
+    rc.set_shard(0, 1, TILE, TILE)
+    rc.enable_counters(True)
+    rc.update_views(WIDTH, HEIGHT, pos[mine], ang[mine], 0.0, 10, MAXLEVEL, BASESIZE, 0)
+    c = rc.read_counters()
+    rc.enable_counters(False)
+    rays = torch.tensor([c["rays_primary"] + c["rays_shadow"] + c["rays_disc"]], dtype=torch.int64, device=dev)
+    ms = []
+    for _ in range(3):
+        rc.update_views(WIDTH, HEIGHT, pos[mine], ang[mine], 0.0, 10, MAXLEVEL, BASESIZE, 0)
+        ms.append(rc.last_frame_ms())
+    t = torch.tensor([float(np.median(ms))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(rays)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return {"views": n, "views_per_gpu": len(mine), "rays": int(rays.item()), "batch_ms": float(t.item()),
+            "ms_per_view": float(t.item()) / n, "mrays_s": int(rays.item()) / float(t.item()) / 1e3,
+            "note": "device time of the slowest rank for its share of the 64 views (1080p each)"}
 
 
 def bench_config(meta, args, world):
@@ -328,6 +404,8 @@ def _main():
     ap.add_argument("--tile", type=int, default=64, help="shard tile edge in pixels (multiple of 16)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--no-c1", action="store_true", help="skip the configs[0] (C1, 640x360) side measurement")
+    ap.add_argument("--c5", action="store_true", help="also measure configs[4]: 64 random views sharded by view")
     args = ap.parse_args()
 
     global DIVISION
@@ -498,6 +576,11 @@ def _main():
                "d2h_bytes_per_step": WIDTH * HEIGHT * 4, "ms_per_step": 1e3 * e2e_s / args.steps,
                "note": "no L2 flush in this leg"}
 
+    c5 = None
+    if args.c5:
+        sharded.close()
+        c5 = c5_views(rc, sc, rank, world, dev, dist, torch)
+
     if rank == 0:
         total_rays = sum(rays_of(per_pose[i % len(poses)]) for i in range(args.steps))
         total_ms = float(step_ms.sum())
@@ -527,6 +610,11 @@ def _main():
             "division": {0: "glsl a*(1/b) (matches the reference shader on llvmpipe bit for bit)",
                          1: "ieee a/b (matches the reference CPU twin)"}[args.division],
         }
+        out["extras"] = {}
+        if c5 is not None:
+            out["extras"]["c5_64_views"] = c5
+        if not args.no_c1 and world == 1:
+            out["extras"]["c1_640x360"] = c1_gpu(K, local)
         if not args.no_cpu and world == 1:
             cores = os.cpu_count() or 1
             rays, dt = 0, 0.0
