@@ -406,10 +406,15 @@ def _main():
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--no-c1", action="store_true", help="skip the configs[0] (C1, 640x360) side measurement")
     ap.add_argument("--c5", action="store_true", help="also measure configs[4]: 64 random views sharded by view")
+    ap.add_argument("--res", default="1080p", choices=["1080p", "4k"],
+                    help="4k = BASELINE configs[2] (3840x2160, tile split); the default is the metric's 1080p")
     args = ap.parse_args()
 
-    global DIVISION
+    global DIVISION, WIDTH, HEIGHT, METRIC
     DIVISION = args.division
+    if args.res == "4k":
+        WIDTH, HEIGHT = 3840, 2160
+        METRIC = "Mrays/s (primary+shadow) at 2160p, 90M-pt octree"
     if args.impl == "reference":
         return reference_arm(args)
 
