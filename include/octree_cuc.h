@@ -217,6 +217,16 @@ void     octree_cuc_ipc_export_frame(octree_glc_t* rc, uint8_t* handle64);
 uint64_t octree_cuc_ipc_open(octree_glc_t* rc, const uint8_t* handle64);
 void     octree_cuc_ipc_close(octree_glc_t* rc, uint64_t device_ptr);
 
+/* Optional: page-lock a host array the caller uploads from every frame (the dynamic octree, the skinning
+ * output) so that bulk uploads run at full PCIe rate instead of through the driver's pageable staging.
+ * The caller guarantees the memory stays allocated until it is unpinned; nothing is pinned implicitly. */
+void octree_cuc_pin_host_buffer(octree_glc_t* rc, void* data, size_t bytes);
+void octree_cuc_unpin_host_buffer(octree_glc_t* rc, void* data);
+
+/* wall-clock milliseconds the connector spent inside upload calls (host side, including the copies it waited
+ * for) since the last call of this function */
+double octree_cuc_take_upload_ms(octree_glc_t* rc);
+
 /* multi-GPU range updates: pending ranges can be exported as one packed blob
  * (header + payload) by the rank that received the host uploads, broadcast by
  * the caller (NCCL), and applied on every other rank. */

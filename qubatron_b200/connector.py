@@ -79,6 +79,9 @@ _PROTOS = {
     "octree_cuc_ipc_export_frame": (None, [C.POINTER(octree_glc_t), C.c_void_p]),
     "octree_cuc_ipc_open": (C.c_uint64, [C.POINTER(octree_glc_t), C.c_void_p]),
     "octree_cuc_ipc_close": (None, [C.POINTER(octree_glc_t), C.c_uint64]),
+    "octree_cuc_pin_host_buffer": (None, [C.POINTER(octree_glc_t), C.c_void_p, C.c_size_t]),
+    "octree_cuc_unpin_host_buffer": (None, [C.POINTER(octree_glc_t), C.c_void_p]),
+    "octree_cuc_take_upload_ms": (C.c_double, [C.POINTER(octree_glc_t)]),
     "octree_cuc_selftest_div": (C.c_uint64, [C.POINTER(octree_glc_t), C.c_uint64, C.c_uint64]),
     "octree_cuc_export_pending": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_void_p, C.c_size_t]),
     "octree_cuc_apply_blob": (None, [C.POINTER(octree_glc_t), C.c_void_p, C.c_size_t]),
@@ -264,6 +267,15 @@ class OctreeGlc:
 
     def ipc_close(self, ptr):
         self.lib.octree_cuc_ipc_close(self._p, int(ptr))
+
+    def pin_host_buffer(self, arr):
+        self.lib.octree_cuc_pin_host_buffer(self._p, arr.ctypes.data_as(C.c_void_p), arr.nbytes)
+
+    def unpin_host_buffer(self, arr):
+        self.lib.octree_cuc_unpin_host_buffer(self._p, arr.ctypes.data_as(C.c_void_p))
+
+    def take_upload_ms(self):
+        return float(self.lib.octree_cuc_take_upload_ms(self._p))
 
     def selftest_div(self, seed, count):
         return int(self.lib.octree_cuc_selftest_div(self._p, int(seed), int(count)))

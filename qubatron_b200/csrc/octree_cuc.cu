@@ -10,6 +10,7 @@
 #include "octree_render.cuh"
 #include "octree_trace_fast.cuh"
 
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -252,6 +253,7 @@ struct Impl
 
     uint64_t launches = 0;
     uint64_t memsize  = 0;
+    double   upload_ms = 0.0; // host wall time spent in upload calls
 };
 
 int g_selected_device = -1;
@@ -876,6 +878,12 @@ void octree_glc_upload_texbuffer_data(octree_glc_t* rc, void* data, int type, si
                                       size_t start, size_t end, octree_glc_buffer_t buftype)
 {
     Impl* I = impl_of(rc);
+    struct Timer
+    {
+        Impl*                                 I;
+        std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+        ~Timer() { I->upload_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+    } timer{I};
     if ((int) buftype < 0 || (int) buftype > 5) die("upload: unknown buffer type");
     if (itemsize == 0 || data == nullptr) return;
     const bool oct = is_octree(buftype);
@@ -1089,6 +1097,27 @@ void octree_cuc_ipc_close(octree_glc_t* rc, uint64_t device_ptr)
     CUDA_OK(cudaStreamSynchronize(I->stream));
     if (I->ext_target == device_ptr) I->ext_target = 0;
     CUDA_OK(cudaIpcCloseMemHandle((void*) (uintptr_t) device_ptr));
+}
+
+void octree_cuc_pin_host_buffer(octree_glc_t* rc, void* data, size_t bytes)
+{
+    impl_of(rc);
+    CUDA_OK(cudaHostRegister(data, bytes, cudaHostRegisterDefault));
+}
+
+void octree_cuc_unpin_host_buffer(octree_glc_t* rc, void* data)
+{
+    Impl* I = impl_of(rc);
+    CUDA_OK(cudaStreamSynchronize(I->stream));
+    CUDA_OK(cudaHostUnregister(data));
+}
+
+double octree_cuc_take_upload_ms(octree_glc_t* rc)
+{
+    Impl*  I  = impl_of(rc);
+    double ms = I->upload_ms;
+    I->upload_ms = 0.0;
+    return ms;
 }
 
 uint64_t octree_cuc_selftest_div(octree_glc_t* rc, uint64_t seed, uint64_t count)
