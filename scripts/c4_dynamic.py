@@ -38,6 +38,7 @@ stat = S.HostOctree()
 t0 = time.time()
 stat.insert_points(np.asarray(sc.pnt_s))
 print("static host tree rebuilt in %.1f s (%d nodes)" % (time.time() - t0, len(stat)), file=sys.stderr)
+xs_sorted = np.maximum.accumulate(np.asarray(sc.pnt_s[:, 0]))  # monotone envelope of the x-major order
 col_s = np.array(sc.col_s)
 nrm_s = np.array(sc.nrm_s)
 fig = np.array(sc.pnt_d)
@@ -66,8 +67,12 @@ for mode in ("pageable", "pinned"):
         dyn_nodes[:ln] = dyn.nodes(copy=False)
         nrm_out[...] = fig_n
         # punch-hole batch on the static tree near the figure
-        centre = np.array([760.0 + 3 * f, 100.0, 260.0], np.float32)
-        cand = np.nonzero(np.linalg.norm(np.asarray(sc.pnt_s[:4000000]) - centre[None, :], axis=1) < 30.0)[0]
+        centre = np.array([760.0 + 3 * f, 62.0, 300.0], np.float32)
+        # points are x-major sorted (qmc): bracket the x slab first
+        lo_i = int(np.searchsorted(xs_sorted, centre[0] - 30.0))
+        hi_i = int(np.searchsorted(xs_sorted, centre[0] + 30.0))
+        slab = np.asarray(sc.pnt_s[lo_i:hi_i])
+        cand = lo_i + np.nonzero(np.linalg.norm(slab - centre[None, :], axis=1) < 30.0)[0]
         victims = cand[rng.permutation(len(cand))[:500]] if len(cand) else []
         edits = []
         touched = []
