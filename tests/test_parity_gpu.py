@@ -398,3 +398,31 @@ def test_dynamic_tree_rebuilt_every_frame(scene_c1):
         seen_dynamic += int((ref["aux"][..., K.AUX_MODEL_D] > 0).sum())
     assert seen_dynamic > 3000
     rc.destroy()
+
+
+def test_c2_full_scale_frames_equal_the_oracle():
+    """BASELINE configs[1] at FULL size: the 95 M-point / 62 M-node level + 10 M-point figure, 1920x1080, all four
+    bench poses -- every pixel's flags (hit / shadow visibility / disc), hit indices and RGBA against the oracle
+    (which needs ~1 s per frame on the box's host cores).  Set QB_TEST_SCALE to shrink the level (same generator)."""
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    scale = float(os.environ.get("QB_TEST_SCALE", "1.0"))
+    sc, meta = bench.get_scene(scale, 0, lambda: None)
+    rc = K.OctreeGlc(b"", device=0)
+    rc.upload_scene(sc)
+    rc.enable_aux(True)
+    rc.enable_counters(True)
+    osc = O.OracleScene(sc)
+    for pose, (pos, ang) in enumerate(sc.cameras):
+        ref = O.render(osc, O.uniforms(1920, 1080, pos, ang))
+        rc.set_kernel(K.KERNEL_AUTO)
+        rc.update(1920, 1080, pos, ang)
+        assert rc.last_kernel() == K.KERNEL_FAST
+        flags, aux = rc.read_aux()
+        out = parity.compare(rc.read_frame(), flags, aux, ref, what="C2 pose %d" % pose)
+        assert out["rgba_maxdiff"] == 0
+        assert rc.read_counters() == ref["counters"]
+    rc.destroy()
