@@ -725,6 +725,7 @@ void render_views(octree_glc_t* rc, int n, float width, float height, const floa
     P.basecube[3] = basesize;
     P.maxlevel    = maxlevel;
     P.leaf_size   = ldexpf(basesize, -maxlevel);
+    P.inv_leaf_size = 1.0f / P.leaf_size;
     P.W           = W;
     P.H           = H;
     P.sx          = ow / (float) W;

@@ -74,6 +74,7 @@ struct FrameParams
     float basecube[4]; // (0, S, S, S), octree_glc.c L263
     int   maxlevel;
     float leaf_size;   // S / 2^maxlevel (fast kernel, exact-grid mode)
+    float inv_leaf_size;
 
     int   W, H;   // viewport in pixels
     float sx, sy; // coord scale = ow / W (1.0 for whole-number render sizes)
