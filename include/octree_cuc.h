@@ -110,6 +110,13 @@ void octree_cuc_frame_size(octree_glc_t* rc, int* width, int* height);
  * synchronises.  Returns bytes written. */
 size_t octree_cuc_read_frame(octree_glc_t* rc, uint8_t* rgba_host, size_t capacity);
 
+/* pipelined readback: queue the copy of the last frame to (page-locked) host memory on a separate copy stream and
+ * return at once; the next octree_glc_update renders into a second framebuffer, so the copy of frame i overlaps the
+ * rendering of frame i+1.  octree_cuc_wait_reads waits for all queued copies.  Returns the bytes that will be
+ * written (0 if the buffer is too small). */
+size_t octree_cuc_read_frame_async(octree_glc_t* rc, uint8_t* rgba_host, size_t capacity);
+void   octree_cuc_wait_reads(octree_glc_t* rc);
+
 /* device address of the RGBA8 frame (valid until the next resize) */
 uint64_t octree_cuc_frame_device(octree_glc_t* rc);
 

@@ -60,6 +60,8 @@ _PROTOS = {
     "octree_cuc_frame_size": (None, [C.POINTER(octree_glc_t), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "octree_cuc_read_frame": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_void_p, C.c_size_t]),
     "octree_cuc_frame_device": (C.c_uint64, [C.POINTER(octree_glc_t)]),
+    "octree_cuc_read_frame_async": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_void_p, C.c_size_t]),
+    "octree_cuc_wait_reads": (None, [C.POINTER(octree_glc_t)]),
     "octree_cuc_set_frame_target": (None, [C.POINTER(octree_glc_t), C.c_uint64, C.c_size_t]),
     "octree_cuc_enable_aux": (None, [C.POINTER(octree_glc_t), C.c_int]),
     "octree_cuc_read_aux": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_void_p, C.c_void_p]),
@@ -185,6 +187,16 @@ class OctreeGlc:
         if got == 0:
             raise RuntimeError("read_frame: no frame or buffer too small")
         return out
+
+    def read_frame_async(self, out):
+        """Queue the copy of the last frame into `out` (page-locked uint8 array); see wait_reads()."""
+        got = self.lib.octree_cuc_read_frame_async(self._p, out.ctypes.data_as(C.c_void_p), out.nbytes)
+        if got == 0:
+            raise RuntimeError("read_frame_async: no frame or buffer too small")
+        return out
+
+    def wait_reads(self):
+        self.lib.octree_cuc_wait_reads(self._p)
 
     def frame_device(self):
         return int(self.lib.octree_cuc_frame_device(self._p))

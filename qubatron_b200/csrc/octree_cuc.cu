@@ -228,6 +228,16 @@ struct Impl
     // frame
     uchar4*             frame       = nullptr;
     size_t              frame_cap   = 0; // pixels
+    // pipelined readback (octree_cuc_read_frame_async): a second framebuffer so that the copy of frame i to the
+    // host overlaps the rendering of frame i+1
+    uchar4*             frame_alt   = nullptr;
+    size_t              frame_alt_cap = 0;
+    bool                ring_on     = false;
+    int                 ring_cur    = 0;      // which of {frame, frame_alt} holds the last rendered frame
+    cudaStream_t        copy_stream = nullptr;
+    cudaEvent_t         ev_render[2] = {};
+    cudaEvent_t         ev_copy[2]   = {};
+    bool                copy_pending[2] = {};
     uint64_t            ext_target  = 0;
     size_t              ext_pitch   = 0;
     uint8_t*            flags       = nullptr;
@@ -653,6 +663,7 @@ void render_views(octree_glc_t* rc, int n, float width, float height, const floa
         if (I->frame)
         {
             CUDA_OK(cudaStreamSynchronize(I->stream));
+            if (I->ring_on) CUDA_OK(cudaStreamSynchronize(I->copy_stream));
             CUDA_OK(cudaFree(I->frame));
             I->memsize -= I->frame_cap * 4;
         }
@@ -738,7 +749,25 @@ void render_views(octree_glc_t* rc, int n, float width, float height, const floa
     }
     else
     {
-        P.frame       = I->frame;
+        if (I->ring_on)
+        {
+            I->ring_cur ^= 1;
+            if (I->ring_cur == 1 && pixels * n > I->frame_alt_cap)
+            {
+                if (I->frame_alt)
+                {
+                    CUDA_OK(cudaStreamSynchronize(I->copy_stream));
+                    CUDA_OK(cudaFree(I->frame_alt));
+                    I->memsize -= I->frame_alt_cap * 4;
+                }
+                CUDA_OK(cudaMalloc(&I->frame_alt, pixels * n * 4));
+                I->frame_alt_cap = pixels * n;
+                I->memsize += I->frame_alt_cap * 4;
+            }
+            // the copy that last read this buffer must be done before the kernel overwrites it
+            if (I->copy_pending[I->ring_cur]) CUDA_OK(cudaStreamWaitEvent(I->stream, I->ev_copy[I->ring_cur], 0));
+        }
+        P.frame       = (I->ring_on && I->ring_cur == 1) ? I->frame_alt : I->frame;
         P.pitch       = W;
         P.view_stride = pixels;
     }
@@ -782,6 +811,7 @@ void render_views(octree_glc_t* rc, int n, float width, float height, const floa
         I->last_kernel = fast ? 2 : 1;
     }
     CUDA_OK(cudaEventRecord(I->ev1, I->stream));
+    if (I->ring_on && !I->ext_target) CUDA_OK(cudaEventRecord(I->ev_render[I->ring_cur], I->stream));
     I->timed = true;
     publish_memsize(rc, I);
 }
@@ -861,6 +891,17 @@ void octree_cuc_destroy(octree_glc_t* rc)
     cudaFreeHost(I->desc_host);
     cudaFree(I->counters);
     if (I->frame) cudaFree(I->frame);
+    if (I->frame_alt) cudaFree(I->frame_alt);
+    if (I->ring_on)
+    {
+        cudaStreamSynchronize(I->copy_stream);
+        for (int i = 0; i < 2; i++)
+        {
+            cudaEventDestroy(I->ev_render[i]);
+            cudaEventDestroy(I->ev_copy[i]);
+        }
+        cudaStreamDestroy(I->copy_stream);
+    }
     if (I->flags) cudaFree(I->flags);
     if (I->aux) cudaFree(I->aux);
     if (I->views_host) cudaFreeHost(I->views_host);
@@ -948,7 +989,8 @@ size_t octree_cuc_read_frame(octree_glc_t* rc, uint8_t* rgba_host, size_t capaci
     size_t bytes = (size_t) I->W * I->H * 4 * (I->n_views ? I->n_views : 1);
     if (I->ext_target) die("read_frame: frame target is external, read it there");
     if (bytes == 0 || capacity < bytes) return 0;
-    CUDA_OK(cudaMemcpyAsync(rgba_host, I->frame, bytes, cudaMemcpyDeviceToHost, I->stream));
+    const uchar4* src = (I->ring_on && I->ring_cur == 1) ? I->frame_alt : I->frame;
+    CUDA_OK(cudaMemcpyAsync(rgba_host, src, bytes, cudaMemcpyDeviceToHost, I->stream));
     CUDA_OK(cudaStreamSynchronize(I->stream));
     return bytes;
 }
@@ -956,7 +998,42 @@ size_t octree_cuc_read_frame(octree_glc_t* rc, uint8_t* rgba_host, size_t capaci
 uint64_t octree_cuc_frame_device(octree_glc_t* rc)
 {
     Impl* I = impl_of(rc);
-    return I->ext_target ? I->ext_target : (uint64_t) (uintptr_t) I->frame;
+    if (I->ext_target) return I->ext_target;
+    return (uint64_t) (uintptr_t) ((I->ring_on && I->ring_cur == 1) ? I->frame_alt : I->frame);
+}
+
+size_t octree_cuc_read_frame_async(octree_glc_t* rc, uint8_t* rgba_host, size_t capacity)
+{
+    Impl*  I     = impl_of(rc);
+    size_t bytes = (size_t) I->W * I->H * 4 * (I->n_views ? I->n_views : 1);
+    if (I->ext_target) die("read_frame_async: frame target is external, read it there");
+    if (bytes == 0 || capacity < bytes) return 0;
+    if (!I->ring_on)
+    {
+        // first use: from now on frames alternate between two buffers; the frame just rendered is in `frame`
+        CUDA_OK(cudaStreamCreateWithFlags(&I->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++)
+        {
+            CUDA_OK(cudaEventCreateWithFlags(&I->ev_render[i], cudaEventDisableTiming));
+            CUDA_OK(cudaEventCreateWithFlags(&I->ev_copy[i], cudaEventDisableTiming));
+        }
+        I->ring_on  = true;
+        I->ring_cur = 0;
+        CUDA_OK(cudaEventRecord(I->ev_render[0], I->stream));
+    }
+    const int     k   = I->ring_cur;
+    const uchar4* src = k == 1 ? I->frame_alt : I->frame;
+    CUDA_OK(cudaStreamWaitEvent(I->copy_stream, I->ev_render[k], 0));
+    CUDA_OK(cudaMemcpyAsync(rgba_host, src, bytes, cudaMemcpyDeviceToHost, I->copy_stream));
+    CUDA_OK(cudaEventRecord(I->ev_copy[k], I->copy_stream));
+    I->copy_pending[k] = true;
+    return bytes;
+}
+
+void octree_cuc_wait_reads(octree_glc_t* rc)
+{
+    Impl* I = impl_of(rc);
+    if (I->ring_on) CUDA_OK(cudaStreamSynchronize(I->copy_stream));
 }
 
 void octree_cuc_set_frame_target(octree_glc_t* rc, uint64_t device_ptr, size_t pitch_pixels)

@@ -426,3 +426,30 @@ def test_c2_full_scale_frames_equal_the_oracle():
         assert out["rgba_maxdiff"] == 0
         assert rc.read_counters() == ref["counters"]
     rc.destroy()
+
+
+def test_pipelined_readback_returns_the_right_frames(scene_random):
+    """octree_cuc_read_frame_async: frame i is copied to the host while frame i+1 renders into the second
+    framebuffer; every host buffer must hold exactly its own frame."""
+    import torch
+    cams = [((760.0, 200.0, 420.0), (-0.05, -0.12, 0.0)), ((800.0, 230.0, 380.0), (-0.6, -0.3, 0.0)),
+            ((700.0, 260.0, 500.0), (0.3, -0.4, 0.0)), ((900.0, 150.0, 300.0), (-1.2, 0.1, 0.0)),
+            ((760.0, 200.0, 420.0), (-0.05, -0.12, 0.0))]
+    W, H = 200, 120
+    rc = K.OctreeGlc(b"", device=0)
+    rc.upload_scene(scene_random)
+    sync = []
+    for pos, ang in cams:
+        rc.update(W, H, pos, ang)
+        sync.append(rc.read_frame().copy())
+    bufs = [torch.empty((H, W, 4), dtype=torch.uint8).pin_memory() for _ in cams]
+    for (pos, ang), b in zip(cams, bufs):
+        rc.update(W, H, pos, ang, shoot=0)
+        rc.read_frame_async(b.numpy())
+    rc.wait_reads()
+    for a, b in zip(sync, bufs):
+        assert np.array_equal(a, b.numpy())
+    # the synchronous read still returns the latest frame once the ring is active
+    rc.update(W, H, *cams[1])
+    assert np.array_equal(rc.read_frame(), sync[1])
+    rc.destroy()
