@@ -224,6 +224,21 @@ void     octree_cuc_ipc_export_frame(octree_glc_t* rc, uint8_t* handle64);
 uint64_t octree_cuc_ipc_open(octree_glc_t* rc, const uint8_t* handle64);
 void     octree_cuc_ipc_close(octree_glc_t* rc, uint64_t device_ptr);
 
+/* "Next" row: build an octree on the GPU from per-point octant paths, with the reference's
+ * node numbering, straight into the traversal layout -- what the engine does on the CPU every frame with
+ * octree_reset + octree_insert_path (qubatron.c L439-452, octree.c L149-180).  oct14 / oct54 / oct94 are the
+ * three int32[4 * n] digit buffers of the skinning pass (skeleton_glc.c L238-245), on the host or
+ * (paths_on_device != 0) already on the device; model index of point i = first_modind + i.  Replaces the
+ * whole tree named by `buftype`; returns the node count. */
+size_t octree_cuc_build_octree_from_paths(octree_glc_t* rc, const int32_t* oct14, const int32_t* oct54,
+                                          const int32_t* oct94, size_t n, int first_modind, int paths_on_device,
+                                          octree_glc_buffer_t buftype);
+
+/* copy a device octree back in the reference's 12-int node format (parity checks); returns the node count,
+ * writes nothing if capacity_nodes is too small */
+size_t octree_cuc_download_octree(octree_glc_t* rc, octree_glc_buffer_t buftype, int32_t* nodes12_host,
+                                  size_t capacity_nodes);
+
 /* Optional: page-lock a host array the caller uploads from every frame (the dynamic octree, the skinning
  * output) so that bulk uploads run at full PCIe rate instead of through the driver's pageable staging.
  * The caller guarantees the memory stays allocated until it is unpinned; nothing is pinned implicitly. */

@@ -81,6 +81,9 @@ _PROTOS = {
     "octree_cuc_ipc_export_frame": (None, [C.POINTER(octree_glc_t), C.c_void_p]),
     "octree_cuc_ipc_open": (C.c_uint64, [C.POINTER(octree_glc_t), C.c_void_p]),
     "octree_cuc_ipc_close": (None, [C.POINTER(octree_glc_t), C.c_uint64]),
+    "octree_cuc_build_octree_from_paths": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_void_p, C.c_void_p, C.c_void_p,
+                                                        C.c_size_t, C.c_int, C.c_int, C.c_int]),
+    "octree_cuc_download_octree": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_int, C.c_void_p, C.c_size_t]),
     "octree_cuc_pin_host_buffer": (None, [C.POINTER(octree_glc_t), C.c_void_p, C.c_size_t]),
     "octree_cuc_unpin_host_buffer": (None, [C.POINTER(octree_glc_t), C.c_void_p]),
     "octree_cuc_take_upload_ms": (C.c_double, [C.POINTER(octree_glc_t)]),
@@ -279,6 +282,28 @@ class OctreeGlc:
 
     def ipc_close(self, ptr):
         self.lib.octree_cuc_ipc_close(self._p, int(ptr))
+
+    def build_octree_from_paths(self, paths, first_modind=0, dynamic=True):
+        """paths: int32 [n,12] octant digits (host).  Builds the tree on the GPU with the reference numbering."""
+        paths = np.ascontiguousarray(paths, dtype=np.int32).reshape(-1, 12)
+        p14 = np.ascontiguousarray(paths[:, 0:4])
+        p54 = np.ascontiguousarray(paths[:, 4:8])
+        p94 = np.ascontiguousarray(paths[:, 8:12])
+        return int(self.lib.octree_cuc_build_octree_from_paths(
+            self._p, p14.ctypes.data_as(C.c_void_p), p54.ctypes.data_as(C.c_void_p), p94.ctypes.data_as(C.c_void_p),
+            len(paths), int(first_modind), 0, DYNAMIC_OCTREE if dynamic else STATIC_OCTREE))
+
+    def build_octree_from_device_paths(self, p14_ptr, p54_ptr, p94_ptr, n, first_modind=0, dynamic=True):
+        return int(self.lib.octree_cuc_build_octree_from_paths(
+            self._p, C.c_void_p(int(p14_ptr)), C.c_void_p(int(p54_ptr)), C.c_void_p(int(p94_ptr)), int(n),
+            int(first_modind), 1, DYNAMIC_OCTREE if dynamic else STATIC_OCTREE))
+
+    def download_octree(self, dynamic=True):
+        bt = DYNAMIC_OCTREE if dynamic else STATIC_OCTREE
+        n = int(self.lib.octree_cuc_download_octree(self._p, bt, None, 0))
+        out = np.zeros((n, 12), dtype=np.int32)
+        self.lib.octree_cuc_download_octree(self._p, bt, out.ctypes.data_as(C.c_void_p), n)
+        return out
 
     def pin_host_buffer(self, arr):
         self.lib.octree_cuc_pin_host_buffer(self._p, arr.ctypes.data_as(C.c_void_p), arr.nbytes)

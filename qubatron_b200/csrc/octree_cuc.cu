@@ -7,6 +7,7 @@
 // needs the GPU aborts with a message if CUDA is unusable.
 #include "../../include/octree_cuc.h"
 
+#include "octree_build.cuh"
 #include "octree_render.cuh"
 #include "octree_trace_fast.cuh"
 
@@ -1196,6 +1197,166 @@ double octree_cuc_take_upload_ms(octree_glc_t* rc)
     double ms = I->upload_ms;
     I->upload_ms = 0.0;
     return ms;
+}
+
+// ---------------------------------------------------------------------------
+// GPU tree build from octant paths (octree_build.cuh) and export in the reference format
+// ---------------------------------------------------------------------------
+} // extern "C"
+
+namespace
+{
+template <class T>
+T* scratch(Impl* I, size_t count)
+{
+    void* p = nullptr;
+    CUDA_OK(cudaMallocAsync(&p, (count ? count : 1) * sizeof(T), I->stream));
+    return (T*) p;
+}
+void            scratch_free(Impl* I, void* p) { CUDA_OK(cudaFreeAsync(p, I->stream)); }
+inline unsigned nblk(size_t n) { return (unsigned) ((n + 255) / 256); }
+} // namespace
+
+extern "C" {
+
+size_t octree_cuc_build_octree_from_paths(octree_glc_t* rc, const int32_t* oct14, const int32_t* oct54,
+                                          const int32_t* oct94, size_t n, int first_modind, int paths_on_device,
+                                          octree_glc_buffer_t buftype)
+{
+    Impl* I = impl_of(rc);
+    if (!is_octree(buftype)) die("build_octree_from_paths: buftype must be an octree buffer");
+    if (n >= ((size_t) 1 << 27)) die("build_octree_from_paths: at most 2^27 points");
+    flush_pending(I);
+    const int    t  = tree_index(buftype);
+    cudaStream_t st = I->stream;
+
+    const int *p14 = oct14, *p54 = oct54, *p94 = oct94;
+    int*       staged = nullptr;
+    if (!paths_on_device && n)
+    {
+        staged = scratch<int>(I, n * 12);
+        CUDA_OK(cudaMemcpyAsync(staged, oct14, n * 16, cudaMemcpyHostToDevice, st));
+        CUDA_OK(cudaMemcpyAsync(staged + n * 4, oct54, n * 16, cudaMemcpyHostToDevice, st));
+        CUDA_OK(cudaMemcpyAsync(staged + n * 8, oct94, n * 16, cudaMemcpyHostToDevice, st));
+        p14 = staged, p54 = staged + n * 4, p94 = staged + n * 8;
+    }
+
+    // temporary tree: children by temporary id, creation key (creator << 4 | level) per node
+    size_t    cap       = n / 4 + 4096;
+    int*      tmp_child = scratch<int>(I, cap * 8);
+    unsigned* tmp_key   = scratch<unsigned>(I, cap);
+    CUDA_OK(cudaMemsetAsync(tmp_child, 0, cap * 8 * sizeof(int), st));
+    int* cur = scratch<int>(I, n);
+    CUDA_OK(cudaMemsetAsync(cur, 0, (n ? n : 1) * sizeof(int), st));
+
+    int    level_base = 0, level_count = 1, next = 1;
+    size_t launches = 0;
+    for (int level = 0; level < BUILD_LEVELS && n > 0; level++)
+    {
+        const size_t slots = (size_t) level_count * 8;
+        int*         table = scratch<int>(I, slots);
+        int*         flags = scratch<int>(I, slots);
+        int*         pos   = scratch<int>(I, slots);
+        build_fill_kernel<<<nblk(slots), 256, 0, st>>>(table, slots, 0x7fffffff);
+        build_propose_kernel<<<nblk(n), 256, 0, st>>>(p14, p54, p94, n, level, cur, level_base, table);
+        build_flags_kernel<<<nblk(slots), 256, 0, st>>>(table, slots, flags);
+        size_t tb = 0;
+        CUDA_OK(cub::DeviceScan::ExclusiveSum(nullptr, tb, flags, pos, (int) slots, st));
+        void* tmp = scratch<char>(I, tb);
+        CUDA_OK(cub::DeviceScan::ExclusiveSum(tmp, tb, flags, pos, (int) slots, st));
+        int last_pos = 0, last_flag = 0;
+        CUDA_OK(cudaMemcpyAsync(&last_pos, pos + slots - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaMemcpyAsync(&last_flag, flags + slots - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaStreamSynchronize(st));
+        const int created = last_pos + last_flag;
+        if ((size_t) next + created > cap)
+        {
+            size_t    ncap = ((size_t) next + created) * 2 + 4096;
+            int*      nc   = scratch<int>(I, ncap * 8);
+            unsigned* nk   = scratch<unsigned>(I, ncap);
+            CUDA_OK(cudaMemsetAsync(nc, 0, ncap * 8 * sizeof(int), st));
+            CUDA_OK(cudaMemcpyAsync(nc, tmp_child, (size_t) next * 8 * sizeof(int), cudaMemcpyDeviceToDevice, st));
+            CUDA_OK(cudaMemcpyAsync(nk, tmp_key, (size_t) next * sizeof(unsigned), cudaMemcpyDeviceToDevice, st));
+            scratch_free(I, tmp_child);
+            scratch_free(I, tmp_key);
+            tmp_child = nc, tmp_key = nk, cap = ncap;
+        }
+        build_create_kernel<<<nblk(slots), 256, 0, st>>>(table, pos, slots, level, level_base, next, tmp_child, tmp_key);
+        build_step_kernel<<<nblk(n), 256, 0, st>>>(p14, p54, p94, n, level, cur, tmp_child);
+        CUDA_OK(cudaGetLastError());
+        launches += 6;
+        scratch_free(I, tmp);
+        scratch_free(I, table);
+        scratch_free(I, flags);
+        scratch_free(I, pos);
+        level_base  = next;
+        level_count = created;
+        next += created;
+        if (created == 0) break;
+    }
+
+    const int total = next; // nodes including the root
+    // reference numbering = rank in (creator, level) order
+    int* final_of_tmp = scratch<int>(I, (size_t) total);
+    if (total > 1)
+    {
+        const int m      = total - 1;
+        int*      ids_in = scratch<int>(I, m);
+        int*      ids_out = scratch<int>(I, m);
+        unsigned* keys_out = scratch<unsigned>(I, m);
+        build_iota_kernel<<<nblk(m), 256, 0, st>>>(ids_in, m, 1);
+        size_t tb = 0;
+        CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, tb, tmp_key + 1, keys_out, ids_in, ids_out, m, 0, 32, st));
+        void* tmp = scratch<char>(I, tb);
+        CUDA_OK(cub::DeviceRadixSort::SortPairs(tmp, tb, tmp_key + 1, keys_out, ids_in, ids_out, m, 0, 32, st));
+        build_rank_kernel<<<nblk(m), 256, 0, st>>>(ids_out, m, final_of_tmp);
+        launches += 3;
+        scratch_free(I, tmp);
+        scratch_free(I, ids_in);
+        scratch_free(I, ids_out);
+        scratch_free(I, keys_out);
+    }
+    else
+        CUDA_OK(cudaMemsetAsync(final_of_tmp, 0, sizeof(int), st));
+
+    // straight into the traversal layout of this tree
+    CUDA_OK(cudaStreamSynchronize(st));
+    ensure_capacity(I, buftype, (size_t) total * 48);
+    build_emit_kernel<<<nblk(total), 256, 0, st>>>(tmp_child, tmp_key, final_of_tmp, total, first_modind,
+                                                   (int4*) I->tree[t].child.ptr, (int*) I->tree[t].model.ptr);
+    CUDA_OK(cudaGetLastError());
+    launches += 1;
+    I->tree[t].nodes = (size_t) total; // like octree_reset + rebuild: the old extent is gone
+    I->launches += launches;
+
+    scratch_free(I, final_of_tmp);
+    scratch_free(I, cur);
+    scratch_free(I, tmp_child);
+    scratch_free(I, tmp_key);
+    if (staged) scratch_free(I, staged);
+    CUDA_OK(cudaStreamSynchronize(st)); // host path arrays have been consumed
+    publish_memsize(rc, I);
+    return (size_t) total;
+}
+
+size_t octree_cuc_download_octree(octree_glc_t* rc, octree_glc_buffer_t buftype, int32_t* nodes12_host,
+                                  size_t capacity_nodes)
+{
+    Impl* I = impl_of(rc);
+    if (!is_octree(buftype)) die("download_octree: buftype must be an octree buffer");
+    flush_pending(I);
+    const int    t = tree_index(buftype);
+    const size_t n = I->tree[t].nodes;
+    if (nodes12_host == nullptr || capacity_nodes < n) return n;
+    int* out = scratch<int>(I, n * 12);
+    export_nodes_kernel<<<nblk(n), 256, 0, I->stream>>>((const int4*) I->tree[t].child.ptr,
+                                                        (const int*) I->tree[t].model.ptr, n, out);
+    CUDA_OK(cudaGetLastError());
+    I->launches++;
+    CUDA_OK(cudaMemcpyAsync(nodes12_host, out, n * 48, cudaMemcpyDeviceToHost, I->stream));
+    scratch_free(I, out);
+    CUDA_OK(cudaStreamSynchronize(I->stream));
+    return n;
 }
 
 uint64_t octree_cuc_selftest_div(octree_glc_t* rc, uint64_t seed, uint64_t count)

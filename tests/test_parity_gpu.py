@@ -453,3 +453,50 @@ def test_pipelined_readback_returns_the_right_frames(scene_random):
     rc.update(W, H, *cams[1])
     assert np.array_equal(rc.read_frame(), sync[1])
     rc.destroy()
+
+
+def test_gpu_tree_build_from_paths_equals_sequential_insert():
+    """octree_cuc_build_octree_from_paths ("next" row 8f #1): node-for-node the array that octree_reset +
+    octree_insert_path (octree.c L149-180; qubatron.c L439-452) produce -- which tests/test_host_model.py pins
+    against the reference's compiled code -- for random digits, for a surface-like figure, for duplicates and
+    for the empty and single-point cases."""
+    rng = np.random.default_rng(31)
+    fig_p, fig_c, fig_n = S.zombie_raw(base=(760.0, 100.0, 230.0), spacing=0.5, shells=3)
+    cases = {
+        "random": rng.integers(0, 8, size=(60000, 12)).astype(np.int32),
+        "figure": S.octant_paths(fig_p),
+        "duplicates": np.repeat(rng.integers(0, 8, size=(500, 12)).astype(np.int32), 7, axis=0),
+        "single": rng.integers(0, 8, size=(1, 12)).astype(np.int32),
+        "empty": np.zeros((0, 12), np.int32),
+    }
+    rc = K.OctreeGlc(b"", device=0)
+    for name, paths in cases.items():
+        host = S.HostOctree()
+        host.insert_paths(paths, first_modind=5)
+        n = rc.build_octree_from_paths(paths, first_modind=5, dynamic=True)
+        got = rc.download_octree(dynamic=True)
+        want = host.nodes()
+        assert n == len(want) == len(got), name
+        assert np.array_equal(got, want), name
+    rc.destroy()
+
+
+def test_render_with_gpu_built_dynamic_tree(scene_c1):
+    """The frame rendered from a dynamic tree built on the GPU equals the oracle's frame for the host-built tree."""
+    fig_p, fig_c, fig_n = S.zombie_raw(base=(760.0, 100.0, 230.0), spacing=0.6, shells=2)
+    fig_p, fig_cf, fig_n = S.voxelise(fig_p, fig_c, fig_n)
+    paths = S.octant_paths(fig_p)
+    host = S.HostOctree()
+    host.insert_paths(paths)
+    rc = K.OctreeGlc(b"", device=0)
+    rc.upload_points(scene_c1.col_s, K.STATIC_COLOR)
+    rc.upload_points(scene_c1.nrm_s, K.STATIC_NORMAL)
+    rc.upload_octree(scene_c1.oct_s)
+    rc.upload_points(fig_cf, K.DYNAMIC_COLOR)
+    rc.upload_points(fig_n, K.DYNAMIC_NORMAL)
+    rc.build_octree_from_paths(paths)
+    sc = S.Scene("gpu-built", scene_c1.pnt_s, scene_c1.col_s, scene_c1.nrm_s, scene_c1.oct_s, fig_p, fig_cf, fig_n,
+                 host.nodes())
+    ref, _ = _render_and_compare(sc, 320, 180, *S.CAMERA_C1, rc=rc)
+    assert (ref["aux"][..., K.AUX_MODEL_D] > 0).sum() > 1000
+    rc.destroy()
