@@ -43,9 +43,15 @@ __global__ void build_propose_kernel(const int* __restrict__ p14, const int* __r
                                      int level_base, int* __restrict__ table)
 {
     size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int d = path_digit(p14, p54, p94, i, level);
-    atomicMin(&table[(size_t) (cur[i] - level_base) * 8 + d], (int) i);
+    // slot this point proposes itself for; points beyond n propose nothing
+    long long slot = -1;
+    if (i < n) slot = (long long) (cur[i] - level_base) * 8 + path_digit(p14, p54, p94, i, level);
+    // Neighbouring points usually share the slot (the model is spatially sorted): within a warp indices
+    // ascend, so only the first lane of a run of equal slots can hold the minimum -- one atomic per run
+    // instead of one per point (the top levels would otherwise serialise 10 M atomics on 8 addresses).
+    const long long prev = __shfl_up_sync(0xffffffffu, slot, 1);
+    const bool      head = (threadIdx.x & 31) == 0 || prev != slot;
+    if (slot >= 0 && head) atomicMin(&table[slot], (int) i);
 }
 
 __global__ void build_flags_kernel(const int* __restrict__ table, size_t slots, int* __restrict__ flags)
