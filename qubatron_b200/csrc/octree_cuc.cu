@@ -849,6 +849,14 @@ octree_glc_t octree_glc_init(char* path)
     else
         CUDA_OK(cudaGetDevice(&I->device));
     CUDA_OK(cudaSetDevice(I->device));
+    {
+        // scratch of the tree build comes from the stream-ordered pool: keep freed blocks cached across
+        // synchronisations (the default threshold of 0 returns them to the driver every time)
+        cudaMemPool_t pool;
+        CUDA_OK(cudaDeviceGetDefaultMemPool(&pool, I->device));
+        uint64_t keep = ~0ull;
+        CUDA_OK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     CUDA_OK(cudaStreamCreateWithFlags(&I->own_stream, cudaStreamNonBlocking));
     I->stream = I->own_stream;
     CUDA_OK(cudaEventCreate(&I->ev0));
