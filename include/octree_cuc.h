@@ -234,6 +234,21 @@ size_t octree_cuc_build_octree_from_paths(octree_glc_t* rc, const int32_t* oct14
                                           const int32_t* oct94, size_t n, int first_modind, int paths_on_device,
                                           octree_glc_buffer_t buftype);
 
+/* "Next" row: the offline voxeliser qmc (qmc.c: grid index at 2 * 2^levels cells per axis,
+ * drop points outside the cube, x-major sort, first point of every occupied cell, colour = uchar / 255.0) and
+ * the bulk tree build (octree_insert_point order) on the GPU, straight into the renderer's arrays.  pos / nrm:
+ * float[3 * n], col_u8: uchar[3 * n] (on the host, or on the device when inputs_on_device != 0).  Fills the
+ * colour/normal arrays and the octree of the static (dynamic = 0) or dynamic model; returns the number of
+ * surviving points.  order_host (int64[n], optional) receives their source indices, pos_host (float[3*n],
+ * optional) their positions -- what qmc writes to the .pnt file. */
+size_t octree_cuc_voxelise_and_build(octree_glc_t* rc, const float* pos, const uint8_t* col_u8, const float* nrm,
+                                     size_t n, int size, int levels, int inputs_on_device, int dynamic,
+                                     int64_t* order_host, float* pos_host);
+
+/* copy the device colour / normal arrays back as float[3] per point (parity checks); returns the point count */
+size_t octree_cuc_download_points(octree_glc_t* rc, int dynamic, float* col_host, float* nrm_host,
+                                  size_t capacity_points);
+
 /* copy a device octree back in the reference's 12-int node format (parity checks); returns the node count,
  * writes nothing if capacity_nodes is too small */
 size_t octree_cuc_download_octree(octree_glc_t* rc, octree_glc_buffer_t buftype, int32_t* nodes12_host,

@@ -83,6 +83,11 @@ _PROTOS = {
     "octree_cuc_ipc_close": (None, [C.POINTER(octree_glc_t), C.c_uint64]),
     "octree_cuc_build_octree_from_paths": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_void_p, C.c_void_p, C.c_void_p,
                                                         C.c_size_t, C.c_int, C.c_int, C.c_int]),
+    "octree_cuc_voxelise_and_build": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_void_p, C.c_void_p, C.c_void_p,
+                                                   C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                                   C.c_void_p]),
+    "octree_cuc_download_points": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_int, C.c_void_p, C.c_void_p,
+                                                C.c_size_t]),
     "octree_cuc_download_octree": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_int, C.c_void_p, C.c_size_t]),
     "octree_cuc_pin_host_buffer": (None, [C.POINTER(octree_glc_t), C.c_void_p, C.c_size_t]),
     "octree_cuc_unpin_host_buffer": (None, [C.POINTER(octree_glc_t), C.c_void_p]),
@@ -297,6 +302,29 @@ class OctreeGlc:
         return int(self.lib.octree_cuc_build_octree_from_paths(
             self._p, C.c_void_p(int(p14_ptr)), C.c_void_p(int(p54_ptr)), C.c_void_p(int(p94_ptr)), int(n),
             int(first_modind), 1, DYNAMIC_OCTREE if dynamic else STATIC_OCTREE))
+
+    def voxelise_and_build(self, pos, col_u8, nrm, size=1800, levels=12, dynamic=False, want_order=True):
+        """qmc + bulk tree build on the GPU from raw host arrays; returns (count, order int64[m], pos f32[m,3])."""
+        pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 3)
+        col = np.ascontiguousarray(col_u8, dtype=np.uint8).reshape(-1, 3)
+        nrm = np.ascontiguousarray(nrm, dtype=np.float32).reshape(-1, 3)
+        n = len(pos)
+        order = np.zeros(n, dtype=np.int64) if want_order else None
+        pout = np.zeros((n, 3), dtype=np.float32) if want_order else None
+        m = int(self.lib.octree_cuc_voxelise_and_build(
+            self._p, pos.ctypes.data_as(C.c_void_p), col.ctypes.data_as(C.c_void_p), nrm.ctypes.data_as(C.c_void_p),
+            n, int(size), int(levels), 0, int(bool(dynamic)),
+            order.ctypes.data_as(C.c_void_p) if want_order else None,
+            pout.ctypes.data_as(C.c_void_p) if want_order else None))
+        return (m, order[:m], pout[:m]) if want_order else (m, None, None)
+
+    def download_points(self, dynamic=False):
+        m = int(self.lib.octree_cuc_download_points(self._p, int(bool(dynamic)), None, None, 0))
+        col = np.zeros((m, 3), dtype=np.float32)
+        nrm = np.zeros((m, 3), dtype=np.float32)
+        self.lib.octree_cuc_download_points(self._p, int(bool(dynamic)), col.ctypes.data_as(C.c_void_p),
+                                            nrm.ctypes.data_as(C.c_void_p), m)
+        return col, nrm
 
     def download_octree(self, dynamic=True):
         bt = DYNAMIC_OCTREE if dynamic else STATIC_OCTREE

@@ -145,3 +145,89 @@ __global__ void export_nodes_kernel(const int4* __restrict__ child, const int* _
 }
 
 } // namespace qb
+
+// ---------------------------------------------------------------------------
+// GPU voxeliser ("next" row SURVEY 8f #3): what the reference's offline tool qmc does
+// (/root/reference/src/qubatron/qmc.c L62-83 grid index and drop, L130-165 + L259
+// x-major sort, L291-327 first point of every occupied cell) followed by the bulk
+// tree build from the survivors' octant digits (octree_insert_point, octree.c L95-147).
+// ---------------------------------------------------------------------------
+namespace qb
+{
+
+// sort key = (xi, yi, zi) packed x-major, 16 bits per axis; points outside the cube get the all-ones key
+__global__ void voxel_key_kernel(const float* __restrict__ pos, size_t n, float precision, int division,
+                                 unsigned long long* __restrict__ keys, unsigned* __restrict__ idx)
+{
+    size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    // qmc.c L62-68: floor(p / precision), evaluated in fp32
+    const float xi = floorf(pos[i * 3 + 0] / precision);
+    const float yi = floorf(pos[i * 3 + 1] / precision);
+    const float zi = floorf(pos[i * 3 + 2] / precision);
+    const float dv = (float) division;
+    const bool  in = xi >= 0.0f && xi < dv && yi >= 0.0f && yi < dv && zi >= 0.0f && zi < dv;
+    keys[i] = in ? ((unsigned long long) xi << 32) | ((unsigned long long) yi << 16) | (unsigned long long) zi
+                 : ~0ull;
+    idx[i]  = (unsigned) i;
+}
+
+// first point of every distinct, valid key (the input order inside a cell is kept by the stable sort)
+__global__ void voxel_flag_kernel(const unsigned long long* __restrict__ keys, size_t n, int* __restrict__ flags)
+{
+    size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long k = keys[i];
+    flags[i]                   = k != ~0ull && (i == 0 || keys[i - 1] != k);
+}
+
+// survivors: point record (colour = uchar / 255.0 in double, qmc.c L52-54; normal), source index, and the
+// octant digits of octree_insert_point (size halves per level; (int)(p / size) % 2, +2 / +4 for the LOWER halves)
+__global__ void voxel_emit_kernel(const float* __restrict__ pos, const unsigned char* __restrict__ col,
+                                  const float* __restrict__ nrm, const unsigned* __restrict__ sorted_idx,
+                                  const int* __restrict__ flags, const int* __restrict__ slot, size_t n,
+                                  float basesize, int levels, float* __restrict__ rec, float* __restrict__ pos_out,
+                                  long long* __restrict__ order, int* __restrict__ p14, int* __restrict__ p54,
+                                  int* __restrict__ p94)
+{
+    size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+    if (i >= n || !flags[i]) return;
+    const size_t src = sorted_idx[i];
+    const size_t j   = (size_t) slot[i];
+    const float  px = pos[src * 3 + 0], py = pos[src * 3 + 1], pz = pos[src * 3 + 2];
+    order[j]           = (long long) src;
+    pos_out[j * 3 + 0] = px;
+    pos_out[j * 3 + 1] = py;
+    pos_out[j * 3 + 2] = pz;
+    float* r           = rec + j * 8;
+    r[0]               = (float) ((double) col[src * 3 + 0] / 255.0);
+    r[1]               = (float) ((double) col[src * 3 + 1] / 255.0);
+    r[2]               = (float) ((double) col[src * 3 + 2] / 255.0);
+    r[3]               = 1.0f;
+    r[4]               = nrm[src * 3 + 0];
+    r[5]               = nrm[src * 3 + 1];
+    r[6]               = nrm[src * 3 + 2];
+    r[7]               = 0.0f;
+    float size = basesize;
+    int   d[12];
+#pragma unroll
+    for (int l = 0; l < 12; l++)
+    {
+        d[l] = 0;
+        if (l < levels)
+        {
+            size    = (float) ((double) size / 2.0); // octree.c L102
+            int o   = ((int) (px / size)) % 2;
+            int yi  = ((int) (py / size)) % 2;
+            int zi  = ((int) (pz / size)) % 2;
+            if (yi == 0) o += 2;
+            if (zi == 0) o += 4;
+            d[l] = o;
+        }
+    }
+    reinterpret_cast<int4*>(p14)[j] = make_int4(d[0], d[1], d[2], d[3]);
+    reinterpret_cast<int4*>(p54)[j] = make_int4(d[4], d[5], d[6], d[7]);
+    reinterpret_cast<int4*>(p94)[j] = make_int4(d[8], d[9], d[10], d[11]);
+}
+
+} // namespace qb

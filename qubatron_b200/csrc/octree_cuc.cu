@@ -1227,28 +1227,16 @@ inline unsigned nblk(size_t n) { return (unsigned) ((n + 255) / 256); }
 
 extern "C" {
 
-size_t octree_cuc_build_octree_from_paths(octree_glc_t* rc, const int32_t* oct14, const int32_t* oct54,
-                                          const int32_t* oct94, size_t n, int first_modind, int paths_on_device,
-                                          octree_glc_buffer_t buftype)
+} // extern "C"
+
+namespace
 {
-    Impl* I = impl_of(rc);
-    if (!is_octree(buftype)) die("build_octree_from_paths: buftype must be an octree buffer");
-    if (n >= ((size_t) 1 << 27)) die("build_octree_from_paths: at most 2^27 points");
-    flush_pending(I);
+// paths on the device -> tree `t` in the traversal layout; returns the node count
+size_t build_from_device_paths(Impl* I, int buftype, const int* p14, const int* p54, const int* p94, size_t n,
+                               int first_modind, int levels)
+{
     const int    t  = tree_index(buftype);
     cudaStream_t st = I->stream;
-
-    const int *p14 = oct14, *p54 = oct54, *p94 = oct94;
-    int*       staged = nullptr;
-    if (!paths_on_device && n)
-    {
-        staged = scratch<int>(I, n * 12);
-        CUDA_OK(cudaMemcpyAsync(staged, oct14, n * 16, cudaMemcpyHostToDevice, st));
-        CUDA_OK(cudaMemcpyAsync(staged + n * 4, oct54, n * 16, cudaMemcpyHostToDevice, st));
-        CUDA_OK(cudaMemcpyAsync(staged + n * 8, oct94, n * 16, cudaMemcpyHostToDevice, st));
-        p14 = staged, p54 = staged + n * 4, p94 = staged + n * 8;
-    }
-
     // temporary tree: children by temporary id, creation key (creator << 4 | level) per node
     size_t    cap       = n / 4 + 4096;
     int*      tmp_child = scratch<int>(I, cap * 8);
@@ -1259,7 +1247,7 @@ size_t octree_cuc_build_octree_from_paths(octree_glc_t* rc, const int32_t* oct14
 
     int    level_base = 0, level_count = 1, next = 1;
     size_t launches = 0;
-    for (int level = 0; level < BUILD_LEVELS && n > 0; level++)
+    for (int level = 0; level < levels && n > 0; level++)
     {
         const size_t slots = (size_t) level_count * 8;
         int*         table = scratch<int>(I, slots);
@@ -1341,10 +1329,144 @@ size_t octree_cuc_build_octree_from_paths(octree_glc_t* rc, const int32_t* oct14
     scratch_free(I, cur);
     scratch_free(I, tmp_child);
     scratch_free(I, tmp_key);
+    return (size_t) total;
+}
+} // namespace
+
+extern "C" {
+
+size_t octree_cuc_build_octree_from_paths(octree_glc_t* rc, const int32_t* oct14, const int32_t* oct54,
+                                          const int32_t* oct94, size_t n, int first_modind, int paths_on_device,
+                                          octree_glc_buffer_t buftype)
+{
+    Impl* I = impl_of(rc);
+    if (!is_octree(buftype)) die("build_octree_from_paths: buftype must be an octree buffer");
+    if (n >= ((size_t) 1 << 28)) die("build_octree_from_paths: at most 2^28 points");
+    flush_pending(I);
+    cudaStream_t st = I->stream;
+
+    const int *p14 = oct14, *p54 = oct54, *p94 = oct94;
+    int*       staged = nullptr;
+    if (!paths_on_device && n)
+    {
+        staged = scratch<int>(I, n * 12);
+        CUDA_OK(cudaMemcpyAsync(staged, oct14, n * 16, cudaMemcpyHostToDevice, st));
+        CUDA_OK(cudaMemcpyAsync(staged + n * 4, oct54, n * 16, cudaMemcpyHostToDevice, st));
+        CUDA_OK(cudaMemcpyAsync(staged + n * 8, oct94, n * 16, cudaMemcpyHostToDevice, st));
+        p14 = staged, p54 = staged + n * 4, p94 = staged + n * 8;
+    }
+    const size_t total = build_from_device_paths(I, buftype, p14, p54, p94, n, first_modind, BUILD_LEVELS);
     if (staged) scratch_free(I, staged);
     CUDA_OK(cudaStreamSynchronize(st)); // host path arrays have been consumed
     publish_memsize(rc, I);
-    return (size_t) total;
+    return total;
+}
+
+size_t octree_cuc_voxelise_and_build(octree_glc_t* rc, const float* pos, const uint8_t* col_u8, const float* nrm,
+                                     size_t n, int size, int levels, int inputs_on_device, int dynamic,
+                                     int64_t* order_host, float* pos_host)
+{
+    Impl* I = impl_of(rc);
+    if (levels < 1 || levels > 12) die("voxelise_and_build: 1 <= levels <= 12");
+    if (n >= ((size_t) 1 << 28)) die("voxelise_and_build: at most 2^28 points");
+    flush_pending(I);
+    cudaStream_t st = I->stream;
+    const int    octbuf = dynamic ? OCTREE_GLC_BUFFER_DYNAMIC_OCTREE : OCTREE_GLC_BUFFER_STATIC_OCTREE;
+    const int    colbuf = dynamic ? OCTREE_GLC_BUFFER_DYNAMIC_COLOR : OCTREE_GLC_BUFFER_STATIC_COLOR;
+    const int    t      = dynamic ? 1 : 0;
+
+    const float*   d_pos = pos;
+    const uint8_t* d_col = col_u8;
+    const float*   d_nrm = nrm;
+    void *         s0 = nullptr, *s1 = nullptr, *s2 = nullptr;
+    if (!inputs_on_device && n)
+    {
+        s0 = scratch<float>(I, n * 3);
+        s1 = scratch<uint8_t>(I, n * 3);
+        s2 = scratch<float>(I, n * 3);
+        CUDA_OK(cudaMemcpyAsync(s0, pos, n * 12, cudaMemcpyHostToDevice, st));
+        CUDA_OK(cudaMemcpyAsync(s1, col_u8, n * 3, cudaMemcpyHostToDevice, st));
+        CUDA_OK(cudaMemcpyAsync(s2, nrm, n * 12, cudaMemcpyHostToDevice, st));
+        d_pos = (const float*) s0, d_col = (const uint8_t*) s1, d_nrm = (const float*) s2;
+    }
+
+    int division = 2;
+    for (int i = 0; i < levels; i++) division *= 2;                // qmc.c L217
+    const float precision = (float) size / (float) division;        // qmc.c L218
+    size_t      m         = 0;
+    if (n)
+    {
+        unsigned long long* keys  = scratch<unsigned long long>(I, n);
+        unsigned long long* keys2 = scratch<unsigned long long>(I, n);
+        unsigned*           idx   = scratch<unsigned>(I, n);
+        unsigned*           idx2  = scratch<unsigned>(I, n);
+        voxel_key_kernel<<<nblk(n), 256, 0, st>>>(d_pos, n, precision, division, keys, idx);
+        size_t tb = 0;
+        CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, tb, keys, keys2, idx, idx2, (long long) n, 0, 48, st));
+        void* tmp = scratch<char>(I, tb);
+        // LSD radix sort is stable: equal cells keep their source order, like the reference's sort + first-of-cell
+        CUDA_OK(cub::DeviceRadixSort::SortPairs(tmp, tb, keys, keys2, idx, idx2, (long long) n, 0, 48, st));
+        int* flags = scratch<int>(I, n);
+        int* slot  = scratch<int>(I, n);
+        voxel_flag_kernel<<<nblk(n), 256, 0, st>>>(keys2, n, flags);
+        size_t tb2 = 0;
+        CUDA_OK(cub::DeviceScan::ExclusiveSum(nullptr, tb2, flags, slot, (long long) n, st));
+        void* tmp2 = scratch<char>(I, tb2);
+        CUDA_OK(cub::DeviceScan::ExclusiveSum(tmp2, tb2, flags, slot, (long long) n, st));
+        int last_slot = 0, last_flag = 0;
+        CUDA_OK(cudaMemcpyAsync(&last_slot, slot + n - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaMemcpyAsync(&last_flag, flags + n - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaStreamSynchronize(st));
+        m = (size_t) last_slot + (size_t) last_flag;
+
+        ensure_capacity(I, colbuf, m * 12);
+        long long* order = scratch<long long>(I, m);
+        float*     pout  = scratch<float>(I, m * 3);
+        int*       p14   = scratch<int>(I, m * 4);
+        int*       p54   = scratch<int>(I, m * 4);
+        int*       p94   = scratch<int>(I, m * 4);
+        voxel_emit_kernel<<<nblk(n), 256, 0, st>>>(d_pos, d_col, d_nrm, idx2, flags, slot, n, (float) size, levels,
+                                                    (float*) I->pts[t].rec.ptr, pout, order, p14, p54, p94);
+        CUDA_OK(cudaGetLastError());
+        I->launches += 5;
+        I->pts[t].points = m;
+        build_from_device_paths(I, octbuf, p14, p54, p94, m, 0, levels);
+        if (order_host) CUDA_OK(cudaMemcpyAsync(order_host, order, m * sizeof(long long), cudaMemcpyDeviceToHost, st));
+        if (pos_host) CUDA_OK(cudaMemcpyAsync(pos_host, pout, m * 12, cudaMemcpyDeviceToHost, st));
+        for (void* p : {(void*) keys, (void*) keys2, (void*) idx, (void*) idx2, tmp, (void*) flags, (void*) slot, tmp2,
+                        (void*) order, (void*) pout, (void*) p14, (void*) p54, (void*) p94})
+            scratch_free(I, p);
+    }
+    else
+    {
+        I->pts[t].points = 0;
+        build_from_device_paths(I, octbuf, nullptr, nullptr, nullptr, 0, 0, levels);
+    }
+    if (s0) scratch_free(I, s0);
+    if (s1) scratch_free(I, s1);
+    if (s2) scratch_free(I, s2);
+    CUDA_OK(cudaStreamSynchronize(st));
+    publish_memsize(rc, I);
+    return m;
+}
+
+size_t octree_cuc_download_points(octree_glc_t* rc, int dynamic, float* col_host, float* nrm_host, size_t capacity_points)
+{
+    Impl*        I = impl_of(rc);
+    const int    t = dynamic ? 1 : 0;
+    const size_t m = I->pts[t].points;
+    if (capacity_points < m || (!col_host && !nrm_host)) return m;
+    flush_pending(I);
+    std::vector<float> rec(m * 8);
+    CUDA_OK(cudaMemcpyAsync(rec.data(), I->pts[t].rec.ptr, m * 32, cudaMemcpyDeviceToHost, I->stream));
+    CUDA_OK(cudaStreamSynchronize(I->stream));
+    for (size_t i = 0; i < m; i++)
+        for (int c = 0; c < 3; c++)
+        {
+            if (col_host) col_host[i * 3 + c] = rec[i * 8 + c];
+            if (nrm_host) nrm_host[i * 3 + c] = rec[i * 8 + 4 + c];
+        }
+    return m;
 }
 
 size_t octree_cuc_download_octree(octree_glc_t* rc, octree_glc_buffer_t buftype, int32_t* nodes12_host,

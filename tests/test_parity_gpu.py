@@ -500,3 +500,42 @@ def test_render_with_gpu_built_dynamic_tree(scene_c1):
     ref, _ = _render_and_compare(sc, 320, 180, *S.CAMERA_C1, rc=rc)
     assert (ref["aux"][..., K.AUX_MODEL_D] > 0).sum() > 1000
     rc.destroy()
+
+
+def test_gpu_voxelise_and_bulk_build_equal_the_host_model():
+    """octree_cuc_voxelise_and_build ("next" row 8f #3): the same survivors in the same order as the qmc rules
+    (host voxeliser, itself byte-identical to the reference qmc binary in tests/test_host_model.py), the same
+    colours / normals, and node-for-node the tree octree_insert_point builds from them; then the frame."""
+    rng = np.random.default_rng(41)
+    pos = (np.array([700.0, 100.0, 300.0]) + rng.uniform(0, 60, size=(150000, 3)) * np.array([1, 0.05, 1])).astype(
+        np.float32)
+    pos[:300] = rng.uniform(-80, 1900, size=(300, 3)).astype(np.float32)  # some outside the cube
+    pos[300:600] = pos[600:900]                                            # exact duplicates
+    col = rng.integers(0, 256, size=(len(pos), 3)).astype(np.uint8)
+    nrm = rng.normal(size=(len(pos), 3)).astype(np.float32)
+    hp, hc, hn = S.voxelise(pos, col, nrm)
+    tree = S.HostOctree()
+    tree.insert_points(hp)
+
+    rc = K.OctreeGlc(b"", device=0)
+    m, order, gp = rc.voxelise_and_build(pos, col, nrm, 1800, 12, dynamic=False)
+    assert m == len(hp)
+    assert np.array_equal(gp, hp)
+    assert np.array_equal(pos[order], hp)
+    gc, gn = rc.download_points(dynamic=False)
+    assert np.array_equal(gc, hc) and np.array_equal(gn, hn)
+    assert np.array_equal(rc.download_octree(dynamic=False), tree.nodes())
+    # and it renders like the host-built scene
+    e3 = np.zeros((0, 3), np.float32)
+    sc = S.Scene("gpu-qmc", hp, hc, hn, tree.nodes(), e3, e3, e3, np.zeros((1, 12), np.int32))
+    rc.upload_octree(np.zeros((1, 12), np.int32), dynamic=True)
+    _render_and_compare(sc, 240, 135, (735.0, 140.0, 380.0), (0.05, -0.35, 0.0), rc=rc)
+    # other depths and the dynamic model
+    for levels in (5, 9):
+        hp2, hc2, hn2 = S.voxelise(pos, col, nrm, 1800, levels)
+        t2 = S.HostOctree(1800.0, levels)
+        t2.insert_points(hp2)
+        m2, order2, gp2 = rc.voxelise_and_build(pos, col, nrm, 1800, levels, dynamic=True)
+        assert m2 == len(hp2) and np.array_equal(gp2, hp2)
+        assert np.array_equal(rc.download_octree(dynamic=True), t2.nodes())
+    rc.destroy()
