@@ -245,6 +245,14 @@ size_t octree_cuc_voxelise_and_build(octree_glc_t* rc, const float* pos, const u
                                      size_t n, int size, int levels, int inputs_on_device, int dynamic,
                                      int64_t* order_host, float* pos_host);
 
+/* "Next" row: a batch of the engine's CPU ray queries octree_trace_line (octree.c L341-537)
+ * against the device copy of ONE tree (dynamic_tree = 0 static, 1 dynamic).  pos / dir: float[3 * n] on the
+ * host.  out_index[i] = oct[8] of the leaf hit or 0; out_tlf (float[4 * n], optional) = the leaf cube, left
+ * untouched for misses like *otlf.  Same arithmetic as the compiled reference (IEEE division, its parallel-ray
+ * sentinel): results are bit-identical to it. */
+void octree_cuc_trace_lines(octree_glc_t* rc, size_t n, const float* pos, const float* dir, int dynamic_tree,
+                            int maxlevel, float basesize, int32_t* out_index, float* out_tlf);
+
 /* copy the device colour / normal arrays back as float[3] per point (parity checks); returns the point count */
 size_t octree_cuc_download_points(octree_glc_t* rc, int dynamic, float* col_host, float* nrm_host,
                                   size_t capacity_points);

@@ -86,6 +86,8 @@ _PROTOS = {
     "octree_cuc_voxelise_and_build": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_void_p, C.c_void_p, C.c_void_p,
                                                    C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                                    C.c_void_p]),
+    "octree_cuc_trace_lines": (None, [C.POINTER(octree_glc_t), C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                      C.c_float, C.c_void_p, C.c_void_p]),
     "octree_cuc_download_points": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_int, C.c_void_p, C.c_void_p,
                                                 C.c_size_t]),
     "octree_cuc_download_octree": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_int, C.c_void_p, C.c_size_t]),
@@ -317,6 +319,19 @@ class OctreeGlc:
             order.ctypes.data_as(C.c_void_p) if want_order else None,
             pout.ctypes.data_as(C.c_void_p) if want_order else None))
         return (m, order[:m], pout[:m]) if want_order else (m, None, None)
+
+    def trace_lines(self, pos, direction, dynamic=False, maxlevel=12, basesize=1800.0, want_tlf=True):
+        """Batched octree_trace_line on one device tree: (index int32[n], tlf float32[n,4] zeros for misses)."""
+        pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 3)
+        direction = np.ascontiguousarray(direction, dtype=np.float32).reshape(-1, 3)
+        n = len(pos)
+        idx = np.zeros(n, dtype=np.int32)
+        tlf = np.zeros((n, 4), dtype=np.float32) if want_tlf else None
+        self.lib.octree_cuc_trace_lines(self._p, n, pos.ctypes.data_as(C.c_void_p),
+                                        direction.ctypes.data_as(C.c_void_p), int(bool(dynamic)), int(maxlevel),
+                                        float(basesize), idx.ctypes.data_as(C.c_void_p),
+                                        tlf.ctypes.data_as(C.c_void_p) if want_tlf else None)
+        return idx, tlf
 
     def download_points(self, dynamic=False):
         m = int(self.lib.octree_cuc_download_points(self._p, int(bool(dynamic)), None, None, 0))

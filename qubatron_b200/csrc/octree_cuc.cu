@@ -1450,6 +1450,45 @@ size_t octree_cuc_voxelise_and_build(octree_glc_t* rc, const float* pos, const u
     return m;
 }
 
+void octree_cuc_trace_lines(octree_glc_t* rc, size_t n, const float* pos, const float* dir, int dynamic_tree,
+                            int maxlevel, float basesize, int32_t* out_index, float* out_tlf)
+{
+    Impl* I = impl_of(rc);
+    if (n == 0) return;
+    if (maxlevel < 0 || maxlevel > GENERIC_STACK - 1) die("trace_lines: maxlevel out of range");
+    flush_pending(I);
+    cudaStream_t st = I->stream;
+    FrameParams  P;
+    memset(&P, 0, sizeof(P));
+    const int t     = dynamic_tree ? 1 : 0;
+    P.tree_s.child  = (const int4*) I->tree[t].child.ptr; // the queried tree in the first slot, nothing in the second
+    P.tree_s.model  = (const int*) I->tree[t].model.ptr;
+    P.tree_s.nodes  = (int) I->tree[t].nodes;
+    P.tree_d.child  = (const int4*) I->tree[t].child.ptr;
+    P.tree_d.model  = (const int*) I->tree[t].model.ptr;
+    P.tree_d.nodes  = 0;
+    P.basecube[0]   = 0.0f;
+    P.basecube[1] = P.basecube[2] = P.basecube[3] = basesize;
+    P.maxlevel                                    = maxlevel;
+    float* d_pos = scratch<float>(I, n * 3);
+    float* d_dir = scratch<float>(I, n * 3);
+    int*   d_idx = scratch<int>(I, n);
+    float* d_tlf = out_tlf ? scratch<float>(I, n * 4) : nullptr;
+    CUDA_OK(cudaMemcpyAsync(d_pos, pos, n * 12, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(d_dir, dir, n * 12, cudaMemcpyHostToDevice, st));
+    if (d_tlf) CUDA_OK(cudaMemcpyAsync(d_tlf, out_tlf, n * 16, cudaMemcpyHostToDevice, st)); // misses keep the caller's values
+    trace_lines_kernel<<<nblk(n), 256, 0, st>>>(P, n, d_pos, d_dir, d_idx, d_tlf);
+    CUDA_OK(cudaGetLastError());
+    I->launches++;
+    CUDA_OK(cudaMemcpyAsync(out_index, d_idx, n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (d_tlf) CUDA_OK(cudaMemcpyAsync(out_tlf, d_tlf, n * 16, cudaMemcpyDeviceToHost, st));
+    scratch_free(I, d_pos);
+    scratch_free(I, d_dir);
+    scratch_free(I, d_idx);
+    if (d_tlf) scratch_free(I, d_tlf);
+    CUDA_OK(cudaStreamSynchronize(st));
+}
+
 size_t octree_cuc_download_points(octree_glc_t* rc, int dynamic, float* col_host, float* nrm_host, size_t capacity_points)
 {
     Impl*        I = impl_of(rc);

@@ -56,6 +56,30 @@ struct GenericTracer
     }
 };
 
+// Batched octree_trace_line ("next" row SURVEY 8f #4): the engine's CPU queries (collision probes qubatron.c
+// L214-240, shooting L268-269, foot IK zombie.c L296/L310, ragdoll L477-486) against ONE tree, with the CPU
+// twin's own quirks (octree.c L302-339 parallel-ray sentinel, L360-386 face tests) and IEEE division: the
+// results equal the reference's compiled function bit for bit.  out_index = oct[8] of the leaf or 0;
+// out_tlf (optional) = the leaf cube, left untouched on a miss like *otlf.
+__global__ void trace_lines_kernel(const FrameParams P, size_t n, const float* __restrict__ pos,
+                                   const float* __restrict__ dir, int* __restrict__ out_index,
+                                   float* __restrict__ out_tlf)
+{
+    size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    RayCounters       cnt;
+    const TraceResult r = trace_generic<DIV_IEEE, false, true>(P, make_float3(pos[i * 3], pos[i * 3 + 1], pos[i * 3 + 2]),
+                                                               make_float3(dir[i * 3], dir[i * 3 + 1], dir[i * 3 + 2]), cnt);
+    out_index[i]        = r.status == 1 ? r.model_s : 0;
+    if (out_tlf && r.status == 1)
+    {
+        out_tlf[i * 4 + 0] = r.tx;
+        out_tlf[i * 4 + 1] = r.ty;
+        out_tlf[i * 4 + 2] = r.tz;
+        out_tlf[i * 4 + 3] = r.tw;
+    }
+}
+
 // pixel of thread `tid` inside the CTA's 16x8 block: each warp covers an 8x4
 // patch (lanes row-major inside it) so the 32 rays of a warp stay coherent
 __device__ __forceinline__ void block_pixel(int tid, int& lx, int& ly)

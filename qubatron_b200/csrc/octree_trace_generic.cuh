@@ -23,6 +23,7 @@ struct TraceResult
     int   status;         // 0 miss, 1 leaf, -1 discard
     int   node_s, node_d; // leaf nodes
     int   model_s, model_d;
+    float tx, ty, tz, tw; // res.tlf: the leaf cube (generic tracer only)
 };
 
 struct RayCounters
@@ -50,10 +51,12 @@ __device__ __forceinline__ float qdiv(float n, float d)
 // ray / axis-plane intersection (octree_fsh.c L62-99): w = (c - o)/d, the other
 // two coordinates o + d*w, the plane coordinate exactly c.  A ray parallel to
 // the plane yields FLT_MAX in every component so all range tests fail.
-template <int DIV>
+template <int DIV, bool TWIN = false>
 __device__ __forceinline__ float4 plane_hit_x(float c, float3 o, float3 d)
 {
-    float4 r = make_float4(FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX);
+    // parallel ray: the shader's sentinel is FLT_MAX in every component (octree_fsh.c L64); the engine's CPU twin
+    // uses (0,0,0,FLT_MAX) (octree.c L304, L317, L330), whose xyz CAN pass a range test -- kept as it is
+    float4 r = TWIN ? make_float4(0.0f, 0.0f, 0.0f, FLT_MAX) : make_float4(FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX);
     if (d.x != 0.0f)
     {
         r.w = qdiv<DIV>(c - o.x, d.x);
@@ -63,10 +66,12 @@ __device__ __forceinline__ float4 plane_hit_x(float c, float3 o, float3 d)
     }
     return r;
 }
-template <int DIV>
+template <int DIV, bool TWIN = false>
 __device__ __forceinline__ float4 plane_hit_y(float c, float3 o, float3 d)
 {
-    float4 r = make_float4(FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX);
+    // parallel ray: the shader's sentinel is FLT_MAX in every component (octree_fsh.c L64); the engine's CPU twin
+    // uses (0,0,0,FLT_MAX) (octree.c L304, L317, L330), whose xyz CAN pass a range test -- kept as it is
+    float4 r = TWIN ? make_float4(0.0f, 0.0f, 0.0f, FLT_MAX) : make_float4(FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX);
     if (d.y != 0.0f)
     {
         r.w = qdiv<DIV>(c - o.y, d.y);
@@ -76,10 +81,12 @@ __device__ __forceinline__ float4 plane_hit_y(float c, float3 o, float3 d)
     }
     return r;
 }
-template <int DIV>
+template <int DIV, bool TWIN = false>
 __device__ __forceinline__ float4 plane_hit_z(float c, float3 o, float3 d)
 {
-    float4 r = make_float4(FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX);
+    // parallel ray: the shader's sentinel is FLT_MAX in every component (octree_fsh.c L64); the engine's CPU twin
+    // uses (0,0,0,FLT_MAX) (octree.c L304, L317, L330), whose xyz CAN pass a range test -- kept as it is
+    float4 r = TWIN ? make_float4(0.0f, 0.0f, 0.0f, FLT_MAX) : make_float4(FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX);
     if (d.z != 0.0f)
     {
         r.w = qdiv<DIV>(c - o.z, d.z);
@@ -218,7 +225,7 @@ __device__ __forceinline__ bool base_cube_entry_q(const float* basecube, float3 
     return true;
 }
 
-template <int DIV>
+template <int DIV, bool TWIN = false>
 __device__ __forceinline__ bool base_cube_entry(const float* basecube, float3 pos, float3 dir, float4& entry)
 {
     Cube c;
@@ -234,18 +241,18 @@ __device__ __forceinline__ bool base_cube_entry(const float* basecube, float3 po
 
 #define QB_FACE(ACT, COND)                                                                                            \
     act = ACT;                                                                                                        \
-    if (COND)                                                                                                         \
+    if ((!TWIN || act.w < FLT_MAX) && (COND)) /* octree.c L360-386 tests w < FLT_MAX on the six faces */            \
     {                                                                                                                 \
         if (hitc == 0) h0 = act;                                                                                      \
         if (hitc == 1) h1 = act;                                                                                      \
         hitc++;                                                                                                       \
     }
-    QB_FACE(plane_hit_z<DIV>(c.z1, pos, dir), in_x(c, act.x) && in_y(c, act.y)) // front
-    QB_FACE(plane_hit_z<DIV>(c.z0, pos, dir), in_x(c, act.x) && in_y(c, act.y)) // back
-    QB_FACE(plane_hit_x<DIV>(c.x0, pos, dir), in_y(c, act.y) && in_z(c, act.z)) // left
-    QB_FACE(plane_hit_x<DIV>(c.x1, pos, dir), in_y(c, act.y) && in_z(c, act.z)) // right
-    QB_FACE(plane_hit_y<DIV>(c.y1, pos, dir), in_x(c, act.x) && in_z(c, act.z)) // top
-    QB_FACE(plane_hit_y<DIV>(c.y0, pos, dir), in_x(c, act.x) && in_z(c, act.z)) // bottom
+    QB_FACE(plane_hit_z<DIV, TWIN>(c.z1, pos, dir), in_x(c, act.x) && in_y(c, act.y)) // front
+    QB_FACE(plane_hit_z<DIV, TWIN>(c.z0, pos, dir), in_x(c, act.x) && in_y(c, act.y)) // back
+    QB_FACE(plane_hit_x<DIV, TWIN>(c.x0, pos, dir), in_y(c, act.y) && in_z(c, act.z)) // left
+    QB_FACE(plane_hit_x<DIV, TWIN>(c.x1, pos, dir), in_y(c, act.y) && in_z(c, act.z)) // right
+    QB_FACE(plane_hit_y<DIV, TWIN>(c.y1, pos, dir), in_x(c, act.x) && in_z(c, act.z)) // top
+    QB_FACE(plane_hit_y<DIV, TWIN>(c.y0, pos, dir), in_x(c, act.x) && in_z(c, act.z)) // bottom
 #undef QB_FACE
 
     if (hitc < 2) return false;                   // L195
@@ -270,7 +277,7 @@ struct GenericLevel
 
 constexpr int GENERIC_STACK = 18; // octree_fsh.c L151
 
-template <int DIV, bool COUNT>
+template <int DIV, bool COUNT, bool TWIN = false>
 __device__ __noinline__ TraceResult trace_generic(const FrameParams& P, float3 pos, float3 dir, RayCounters& cnt)
 {
     TraceResult res;
@@ -278,9 +285,10 @@ __device__ __noinline__ TraceResult trace_generic(const FrameParams& P, float3 p
     res.status                       = 0;
     res.node_s = res.node_d = -1;
     res.model_s = res.model_d = 0;
+    res.tx = res.ty = res.tz = res.tw = 0.0f;
 
     float4 entry;
-    if (!base_cube_entry<DIV>(P.basecube, pos, dir, entry))
+    if (!base_cube_entry<DIV, TWIN>(P.basecube, pos, dir, entry))
     {
         res.status = -1;
         return res;
@@ -309,6 +317,7 @@ __device__ __noinline__ TraceResult trace_generic(const FrameParams& P, float3 p
             res.iz      = isp.z;
             res.iw      = isp.w;
             res.status  = 1;
+            res.tx = tlf.x, res.ty = tlf.y, res.tz = tlf.z, res.tw = tlf.w;
             res.node_s  = stck[level].socti;
             res.node_d  = stck[level].docti;
             res.model_s = model_of(P.tree_s, res.node_s, level);
@@ -356,11 +365,11 @@ __device__ __noinline__ TraceResult trace_generic(const FrameParams& P, float3 p
             int    hc = 1;
             hp[0]     = stck[level].isps[0];
             float4 act;
-            act = plane_hit_z<DIV>(hz, pos, dir);
+            act = plane_hit_z<DIV, TWIN>(hz, pos, dir);
             if (act.w > 0.0f && in_x(c, act.x) && in_y(c, act.y)) hp[hc++] = act;
-            act = plane_hit_x<DIV>(hx, pos, dir);
+            act = plane_hit_x<DIV, TWIN>(hx, pos, dir);
             if (act.w > 0.0f && in_y(c, act.y) && in_z(c, act.z)) hp[hc++] = act;
-            act = plane_hit_y<DIV>(hy, pos, dir);
+            act = plane_hit_y<DIV, TWIN>(hy, pos, dir);
             if (act.w > 0.0f && in_x(c, act.x) && in_z(c, act.z)) hp[hc++] = act;
 
             int pre  = -1;

@@ -539,3 +539,37 @@ def test_gpu_voxelise_and_bulk_build_equal_the_host_model():
         assert m2 == len(hp2) and np.array_equal(gp2, hp2)
         assert np.array_equal(rc.download_octree(dynamic=True), t2.nodes())
     rc.destroy()
+
+
+needs_ref = pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built (no /root/reference)")
+
+
+@needs_ref
+def test_batched_trace_lines_equal_the_reference_cpu_function(scene_c1, scene_random):
+    """octree_cuc_trace_lines ("next" row 8f #4) against the reference's own compiled octree_trace_line
+    (oracle/_ref, octree.c unmodified) on the same rays: camera rays, shadow-like rays from the light, rays with
+    zero direction components (the CPU twin's (0,0,0,FLT_MAX) sentinel), rays from outside the cube; static and
+    dynamic tree.  Hit index and leaf cube must be identical."""
+    rng = np.random.default_rng(51)
+    n = 40000
+    org = np.stack([rng.uniform(600, 900, n), rng.uniform(100, 250, n), rng.uniform(100, 450, n)], axis=1).astype(
+        np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d[:2000, 0] = 0.0                       # parallel to the x planes
+    d[2000:4000, 1] = 0.0
+    d[4000:5000, :2] = 0.0                  # along z only
+    org[5000:7000] += np.float32(2500.0)    # outside the cube
+    cases = [(scene_c1.pnt_s, scene_c1.oct_s, False), (scene_random.pnt_d, scene_random.oct_d, True)]
+    rc = K.OctreeGlc(b"", device=0)
+    for pts, nodes, dyn in cases:
+        ref = O.RefOctree()
+        ref.insert_points(pts)
+        assert np.array_equal(ref.nodes(), nodes)
+        rc.upload_octree(nodes, dynamic=dyn)
+        want_idx, want_tlf = ref.trace(org, d)
+        got_idx, got_tlf = rc.trace_lines(org, d, dynamic=dyn)
+        assert (want_idx != 0).sum() > 500
+        assert np.array_equal(got_idx, want_idx)
+        hit = want_idx != 0
+        assert np.array_equal(got_tlf[hit], want_tlf[hit])
+    rc.destroy()
