@@ -247,12 +247,12 @@ __device__ __forceinline__ bool base_cube_entry(const float* basecube, float3 po
         if (hitc == 1) h1 = act;                                                                                      \
         hitc++;                                                                                                       \
     }
-    QB_FACE(plane_hit_z<DIV, TWIN>(c.z1, pos, dir), in_x(c, act.x) && in_y(c, act.y)) // front
-    QB_FACE(plane_hit_z<DIV, TWIN>(c.z0, pos, dir), in_x(c, act.x) && in_y(c, act.y)) // back
-    QB_FACE(plane_hit_x<DIV, TWIN>(c.x0, pos, dir), in_y(c, act.y) && in_z(c, act.z)) // left
-    QB_FACE(plane_hit_x<DIV, TWIN>(c.x1, pos, dir), in_y(c, act.y) && in_z(c, act.z)) // right
-    QB_FACE(plane_hit_y<DIV, TWIN>(c.y1, pos, dir), in_x(c, act.x) && in_z(c, act.z)) // top
-    QB_FACE(plane_hit_y<DIV, TWIN>(c.y0, pos, dir), in_x(c, act.x) && in_z(c, act.z)) // bottom
+    QB_FACE((plane_hit_z<DIV, TWIN>(c.z1, pos, dir)), in_x(c, act.x) && in_y(c, act.y)) // front
+    QB_FACE((plane_hit_z<DIV, TWIN>(c.z0, pos, dir)), in_x(c, act.x) && in_y(c, act.y)) // back
+    QB_FACE((plane_hit_x<DIV, TWIN>(c.x0, pos, dir)), in_y(c, act.y) && in_z(c, act.z)) // left
+    QB_FACE((plane_hit_x<DIV, TWIN>(c.x1, pos, dir)), in_y(c, act.y) && in_z(c, act.z)) // right
+    QB_FACE((plane_hit_y<DIV, TWIN>(c.y1, pos, dir)), in_x(c, act.x) && in_z(c, act.z)) // top
+    QB_FACE((plane_hit_y<DIV, TWIN>(c.y0, pos, dir)), in_x(c, act.x) && in_z(c, act.z)) // bottom
 #undef QB_FACE
 
     if (hitc < 2) return false;                   // L195
