@@ -566,9 +566,12 @@ def test_batched_trace_lines_equal_the_reference_cpu_function(scene_c1, scene_ra
         ref.insert_points(pts)
         assert np.array_equal(ref.nodes(), nodes)
         rc.upload_octree(nodes, dynamic=dyn)
-        want_idx, want_tlf = ref.trace(org, d)
-        got_idx, got_tlf = rc.trace_lines(org, d, dynamic=dyn)
-        assert (want_idx != 0).sum() > 500
+        dd = d.copy()
+        aim = rng.integers(0, len(pts), n // 2)   # half of the rays aim at points of the model
+        dd[n // 2:] = (np.asarray(pts)[aim] - org[n // 2:]).astype(np.float32)
+        want_idx, want_tlf = ref.trace(org, dd)
+        got_idx, got_tlf = rc.trace_lines(org, dd, dynamic=dyn)
+        assert (want_idx != 0).sum() > 5000
         assert np.array_equal(got_idx, want_idx)
         hit = want_idx != 0
         assert np.array_equal(got_tlf[hit], want_tlf[hit])
