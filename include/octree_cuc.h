@@ -234,6 +234,24 @@ size_t octree_cuc_build_octree_from_paths(octree_glc_t* rc, const int32_t* oct14
                                           const int32_t* oct94, size_t n, int first_modind, int paths_on_device,
                                           octree_glc_buffer_t buftype);
 
+/* "Next" row (first half): the skinning / octant-path pass of the reference's skeleton connector
+ * (shaders/skeleton_vsh.c, dispatched by skeleton_glc.c L222-251) on the GPU, outputs kept on the device.
+ *   octree_cuc_skeleton_alloc_in   replaces skeleton_glc_alloc_in (skeleton_glc.c L262): rest-pose points and
+ *                                  normals, float[3] each, `bytes` = size of ONE of the two arrays
+ *   octree_cuc_skeleton_update     replaces the transform-feedback draw: oldbones / newbones = 20 x vec4
+ *                                  (zombie.oribones / newbones); skins points [0, model_count), writes their
+ *                                  normals into the dynamic model and, with build_tree != 0, rebuilds the dynamic
+ *                                  octree from their digits (what qubatron.c L439-452 + L508-529 do through the
+ *                                  host).  Returns the node count of the rebuilt tree (0 if not built).
+ *   octree_cuc_skeleton_read_out   the buffers the reference reads back every frame (skeleton_glc.c L238-245):
+ *                                  oct14 / oct54 / oct94 (int32[4 * n]), normals and skinned points (float[3 * n]),
+ *                                  any pointer may be NULL; returns n */
+void   octree_cuc_skeleton_alloc_in(octree_glc_t* rc, const float* pntdata, const float* nrmdata, size_t bytes);
+size_t octree_cuc_skeleton_update(octree_glc_t* rc, const float* oldbones80, const float* newbones80, int model_count,
+                                  int maxlevel, float basesize, int build_tree);
+size_t octree_cuc_skeleton_read_out(octree_glc_t* rc, int32_t* oct14, int32_t* oct54, int32_t* oct94, float* nrm_out,
+                                    float* pnt_out);
+
 /* "Next" row: the offline voxeliser qmc (qmc.c: grid index at 2 * 2^levels cells per axis,
  * drop points outside the cube, x-major sort, first point of every occupied cell, colour = uchar / 255.0) and
  * the bulk tree build (octree_insert_point order) on the GPU, straight into the renderer's arrays.  pos / nrm:

@@ -73,6 +73,8 @@ def lib(div=DIV_GLSL):
         l.qb_oracle_trace_batch.argtypes = [C.POINTER(_Scene), C.POINTER(Uniforms), C.c_int64, C.c_void_p, C.c_void_p,
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         l.qb_oracle_pixel_ray.argtypes = [C.POINTER(Uniforms), C.c_int, C.c_int, C.c_void_p]
+        l.qb_oracle_skin.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p]
         _libs[div] = l
     return _libs[div]
 
@@ -135,6 +137,22 @@ def trace_batch(oscene, u, pos, direction, threads=0, div=DIV_GLSL):
     lib(div).qb_oracle_trace_batch(C.byref(oscene.c), C.byref(u), n, _ptr(pos), _ptr(direction), _ptr(result),
                                    _ptr(nodes), _ptr(models), _ptr(isp), int(threads))
     return result, nodes, models, isp
+
+
+def skin(oldbones, newbones, positions, normals, maxlevel=12, basesize=1800.0, div=DIV_GLSL):
+    """skeleton_vsh.c main() for n points: (digits int32[n,12], normal_out f32[n,3], skinned point f32[n,3])."""
+    ob = np.ascontiguousarray(oldbones, dtype=np.float32).reshape(20, 4)
+    nb = np.ascontiguousarray(newbones, dtype=np.float32).reshape(20, 4)
+    pos = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
+    nrm = np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 3)
+    n = len(pos)
+    cube = np.array([0.0, basesize, basesize, basesize], dtype=np.float32)
+    digits = np.zeros((n, 12), dtype=np.int32)
+    nout = np.zeros((n, 3), dtype=np.float32)
+    pout = np.zeros((n, 3), dtype=np.float32)
+    lib(div).qb_oracle_skin(_ptr(ob), _ptr(nb), _ptr(cube), int(maxlevel), n, _ptr(pos), _ptr(nrm), _ptr(digits),
+                            _ptr(nout), _ptr(pout))
+    return digits, nout, pout
 
 
 def pixel_rays(u):

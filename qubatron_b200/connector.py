@@ -83,6 +83,11 @@ _PROTOS = {
     "octree_cuc_ipc_close": (None, [C.POINTER(octree_glc_t), C.c_uint64]),
     "octree_cuc_build_octree_from_paths": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_void_p, C.c_void_p, C.c_void_p,
                                                         C.c_size_t, C.c_int, C.c_int, C.c_int]),
+    "octree_cuc_skeleton_alloc_in": (None, [C.POINTER(octree_glc_t), C.c_void_p, C.c_void_p, C.c_size_t]),
+    "octree_cuc_skeleton_update": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                                C.c_float, C.c_int]),
+    "octree_cuc_skeleton_read_out": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_void_p, C.c_void_p, C.c_void_p,
+                                                  C.c_void_p, C.c_void_p]),
     "octree_cuc_voxelise_and_build": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_void_p, C.c_void_p, C.c_void_p,
                                                    C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                                    C.c_void_p]),
@@ -304,6 +309,31 @@ class OctreeGlc:
         return int(self.lib.octree_cuc_build_octree_from_paths(
             self._p, C.c_void_p(int(p14_ptr)), C.c_void_p(int(p54_ptr)), C.c_void_p(int(p94_ptr)), int(n),
             int(first_modind), 1, DYNAMIC_OCTREE if dynamic else STATIC_OCTREE))
+
+    def skeleton_alloc_in(self, pnt, nrm):
+        pnt = np.ascontiguousarray(pnt, dtype=np.float32).reshape(-1, 3)
+        nrm = np.ascontiguousarray(nrm, dtype=np.float32).reshape(-1, 3)
+        assert pnt.shape == nrm.shape
+        self.lib.octree_cuc_skeleton_alloc_in(self._p, pnt.ctypes.data_as(C.c_void_p), nrm.ctypes.data_as(C.c_void_p),
+                                              pnt.nbytes)
+        self._skin_n = len(pnt)
+
+    def skeleton_update(self, oldbones, newbones, model_count=None, maxlevel=12, basesize=1800.0, build_tree=True):
+        ob = np.ascontiguousarray(oldbones, dtype=np.float32).reshape(20, 4)
+        nb = np.ascontiguousarray(newbones, dtype=np.float32).reshape(20, 4)
+        n = self._skin_n if model_count is None else int(model_count)
+        return int(self.lib.octree_cuc_skeleton_update(self._p, ob.ctypes.data_as(C.c_void_p),
+                                                       nb.ctypes.data_as(C.c_void_p), n, int(maxlevel),
+                                                       float(basesize), int(bool(build_tree))))
+
+    def skeleton_read_out(self, n):
+        p14, p54, p94 = (np.zeros((n, 4), np.int32) for _ in range(3))
+        nrm = np.zeros((n, 3), np.float32)
+        pnt = np.zeros((n, 3), np.float32)
+        self.lib.octree_cuc_skeleton_read_out(self._p, p14.ctypes.data_as(C.c_void_p), p54.ctypes.data_as(C.c_void_p),
+                                              p94.ctypes.data_as(C.c_void_p), nrm.ctypes.data_as(C.c_void_p),
+                                              pnt.ctypes.data_as(C.c_void_p))
+        return np.concatenate([p14, p54, p94], axis=1), nrm, pnt
 
     def voxelise_and_build(self, pos, col_u8, nrm, size=1800, levels=12, dynamic=False, want_order=True):
         """qmc + bulk tree build on the GPU from raw host arrays; returns (count, order int64[m], pos f32[m,3])."""

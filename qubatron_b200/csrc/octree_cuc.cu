@@ -10,6 +10,7 @@
 #include "octree_build.cuh"
 #include "octree_render.cuh"
 #include "octree_trace_fast.cuh"
+#include "skeleton_skin.cuh"
 
 #include <chrono>
 #include <cmath>
@@ -261,6 +262,14 @@ struct Impl
     int   kernel_choice  = 0;
     int   last_kernel    = 0;
     int   div_mode       = DIV_GLSL; // division semantics, octree_trace_generic.cuh
+
+    // skinning ("next" row 8f #1): inputs uploaded once, outputs kept on the device
+    float* skin_pos = nullptr;
+    float* skin_nrm = nullptr;
+    size_t skin_n   = 0;
+    int4 * skin_p14 = nullptr, *skin_p54 = nullptr, *skin_p94 = nullptr;
+    float* skin_pnt_out = nullptr;
+    size_t skin_count   = 0; // points of the last update
 
     uint64_t launches = 0;
     uint64_t memsize  = 0;
@@ -901,6 +910,9 @@ void octree_cuc_destroy(octree_glc_t* rc)
     cudaFree(I->counters);
     if (I->frame) cudaFree(I->frame);
     if (I->frame_alt) cudaFree(I->frame_alt);
+    for (void* p : {(void*) I->skin_pos, (void*) I->skin_nrm, (void*) I->skin_p14, (void*) I->skin_p54,
+                    (void*) I->skin_p94, (void*) I->skin_pnt_out})
+        if (p) cudaFree(p);
     if (I->ring_on)
     {
         cudaStreamSynchronize(I->copy_stream);
@@ -1448,6 +1460,162 @@ size_t octree_cuc_voxelise_and_build(octree_glc_t* rc, const float* pos, const u
     CUDA_OK(cudaStreamSynchronize(st));
     publish_memsize(rc, I);
     return m;
+}
+
+} // extern "C"
+
+namespace
+{
+struct h3
+{
+    float x, y, z;
+};
+// host fp32 helpers with separately rounded operations (the file is built with -ffp-contract=off)
+inline h3    hsub(h3 a, h3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline h3    hadd(h3 a, h3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline float hdot(h3 a, h3 b)
+{
+    volatile float x = a.x * b.x, y = a.y * b.y, z = a.z * b.z;
+    volatile float s = x + y;
+    return s + z;
+}
+inline float hlen(h3 a) { return sqrtf(hdot(a, a)); }
+inline float hdiv(float a, float b, int div)
+{
+    if (div == DIV_GLSL)
+    {
+        volatile float r = 1.0f / b;
+        return a * r;
+    }
+    return a / b;
+}
+inline h3 hdiv3(h3 a, float f, int div) { return {hdiv(a.x, f, div), hdiv(a.y, f, div), hdiv(a.z, f, div)}; }
+inline h3 hcross(h3 a, h3 b)
+{
+    volatile float x1 = a.y * b.z, x2 = b.y * a.z, y1 = a.z * b.x, y2 = b.z * a.x, z1 = a.x * b.y, z2 = b.x * a.y;
+    return {x1 - x2, y1 - y2, z1 - z2};
+}
+inline void hquat(h3 axis, float angle, float* q)
+{
+    volatile float h = angle * 0.5f;
+    const float    sn = sinf(h), cs = cosf(h);
+    volatile float x = axis.x * sn, y = axis.y * sn, z = axis.z * sn;
+    q[0] = x, q[1] = y, q[2] = z, q[3] = cs;
+}
+
+// skeleton_vsh.c L92-93, L103, L119, L132-151 for one bone pair: everything that does not depend on the point
+void bone_consts(const float* ob, const float* nb, int div, BoneConsts* out10)
+{
+    for (int k = 0; k < 10; k++)
+    {
+        const int   i = 2 * k;
+        BoneConsts& c = out10[k];
+        memset(&c, 0, sizeof(c));
+        h3 a = {ob[i * 4], ob[i * 4 + 1], ob[i * 4 + 2]}, b = {ob[i * 4 + 4], ob[i * 4 + 5], ob[i * 4 + 6]};
+        h3 oldbone = hsub(b, a);
+        h3 midp    = hadd(a, hdiv3(oldbone, 2.0f, div));
+        h3 na = {nb[i * 4], nb[i * 4 + 1], nb[i * 4 + 2]}, nbb = {nb[i * 4 + 4], nb[i * 4 + 5], nb[i * 4 + 6]};
+        h3 currbone = hsub(nbb, na);
+        h3 on       = hdiv3(oldbone, hlen(oldbone), div);
+        h3 cn       = hdiv3(currbone, hlen(currbone), div);
+        c.a[0] = a.x, c.a[1] = a.y, c.a[2] = a.z;
+        c.b[0] = b.x, c.b[1] = b.y, c.b[2] = b.z;
+        c.effect     = ob[i * 4 + 3];
+        c.oldbone[0] = oldbone.x, c.oldbone[1] = oldbone.y, c.oldbone[2] = oldbone.z;
+        c.midp[0] = midp.x, c.midp[1] = midp.y, c.midp[2] = midp.z;
+        c.half_len = hdiv(hlen(oldbone), 2.0f, div);
+        c.ab_dot   = hdot(oldbone, oldbone);
+        c.newa[0] = na.x, c.newa[1] = na.y, c.newa[2] = na.z;
+        hquat(on, nb[i * 4 + 3], c.rot_quat);
+        const float bones_dot   = hdot(on, cn);
+        const float bones_angle = acosf(bones_dot);
+        const h3    axis        = hcross(on, cn);
+        c.has_axis              = hlen(axis) > 0.000001f;
+        if (c.has_axis) hquat(hdiv3(axis, hlen(axis), div), bones_angle, c.axis_quat);
+    }
+}
+} // namespace
+
+extern "C" {
+
+void octree_cuc_skeleton_alloc_in(octree_glc_t* rc, const float* pntdata, const float* nrmdata, size_t bytes)
+{
+    Impl*        I = impl_of(rc);
+    const size_t n = bytes / 12;
+    CUDA_OK(cudaStreamSynchronize(I->stream));
+    for (void* p : {(void*) I->skin_pos, (void*) I->skin_nrm, (void*) I->skin_p14, (void*) I->skin_p54,
+                    (void*) I->skin_p94, (void*) I->skin_pnt_out})
+        if (p) CUDA_OK(cudaFree(p));
+    I->memsize -= I->skin_n * (12 + 12 + 48 + 12);
+    I->skin_n = n;
+    CUDA_OK(cudaMalloc(&I->skin_pos, (n ? n : 1) * 12));
+    CUDA_OK(cudaMalloc(&I->skin_nrm, (n ? n : 1) * 12));
+    CUDA_OK(cudaMalloc(&I->skin_p14, (n ? n : 1) * 16));
+    CUDA_OK(cudaMalloc(&I->skin_p54, (n ? n : 1) * 16));
+    CUDA_OK(cudaMalloc(&I->skin_p94, (n ? n : 1) * 16));
+    CUDA_OK(cudaMalloc(&I->skin_pnt_out, (n ? n : 1) * 12));
+    I->memsize += n * (12 + 12 + 48 + 12);
+    CUDA_OK(cudaMemcpyAsync(I->skin_pos, pntdata, n * 12, cudaMemcpyHostToDevice, I->stream));
+    CUDA_OK(cudaMemcpyAsync(I->skin_nrm, nrmdata, n * 12, cudaMemcpyHostToDevice, I->stream));
+    CUDA_OK(cudaStreamSynchronize(I->stream));
+    ensure_capacity(I, OCTREE_GLC_BUFFER_DYNAMIC_NORMAL, n * 12);
+    publish_memsize(rc, I);
+}
+
+size_t octree_cuc_skeleton_update(octree_glc_t* rc, const float* oldbones80, const float* newbones80, int model_count,
+                                  int maxlevel, float basesize, int build_tree)
+{
+    Impl* I = impl_of(rc);
+    if (model_count < 0 || (size_t) model_count > I->skin_n) die("skeleton_update: more points than skeleton_alloc_in gave");
+    if (maxlevel < 1 || maxlevel > 12) die("skeleton_update: 1 <= maxlevel <= 12");
+    flush_pending(I);
+    SkinParams S;
+    bone_consts(oldbones80, newbones80, I->div_mode, S.bones);
+    S.basesize = basesize;
+    S.maxlevel = maxlevel;
+    const size_t n = (size_t) model_count;
+    size_t       nodes = 0;
+    if (n)
+    {
+        float* rec = (float*) I->pts[1].rec.ptr;
+        if (I->div_mode == DIV_GLSL)
+            skin_kernel<DIV_GLSL><<<nblk(n), 256, 0, I->stream>>>(S, n, I->skin_pos, I->skin_nrm, I->skin_p14,
+                                                                  I->skin_p54, I->skin_p94, rec, I->skin_pnt_out);
+        else
+            skin_kernel<DIV_IEEE><<<nblk(n), 256, 0, I->stream>>>(S, n, I->skin_pos, I->skin_nrm, I->skin_p14,
+                                                                  I->skin_p54, I->skin_p94, rec, I->skin_pnt_out);
+        CUDA_OK(cudaGetLastError());
+        I->launches++;
+        if (n > I->pts[1].points) I->pts[1].points = n;
+    }
+    I->skin_count = n;
+    if (build_tree)
+        nodes = build_from_device_paths(I, OCTREE_GLC_BUFFER_DYNAMIC_OCTREE, (const int*) I->skin_p14,
+                                        (const int*) I->skin_p54, (const int*) I->skin_p94, n, 0, maxlevel);
+    publish_memsize(rc, I);
+    return nodes;
+}
+
+size_t octree_cuc_skeleton_read_out(octree_glc_t* rc, int32_t* oct14, int32_t* oct54, int32_t* oct94, float* nrm_out,
+                                    float* pnt_out)
+{
+    Impl*        I = impl_of(rc);
+    const size_t n = I->skin_count;
+    cudaStream_t st = I->stream;
+    if (oct14) CUDA_OK(cudaMemcpyAsync(oct14, I->skin_p14, n * 16, cudaMemcpyDeviceToHost, st));
+    if (oct54) CUDA_OK(cudaMemcpyAsync(oct54, I->skin_p54, n * 16, cudaMemcpyDeviceToHost, st));
+    if (oct94) CUDA_OK(cudaMemcpyAsync(oct94, I->skin_p94, n * 16, cudaMemcpyDeviceToHost, st));
+    if (pnt_out) CUDA_OK(cudaMemcpyAsync(pnt_out, I->skin_pnt_out, n * 12, cudaMemcpyDeviceToHost, st));
+    if (nrm_out)
+    {
+        std::vector<float> rec(n * 8);
+        CUDA_OK(cudaMemcpyAsync(rec.data(), I->pts[1].rec.ptr, n * 32, cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaStreamSynchronize(st));
+        for (size_t i = 0; i < n; i++)
+            for (int c = 0; c < 3; c++) nrm_out[i * 3 + c] = rec[i * 8 + 4 + c];
+    }
+    CUDA_OK(cudaStreamSynchronize(st));
+    return n;
 }
 
 void octree_cuc_trace_lines(octree_glc_t* rc, size_t n, const float* pos, const float* dir, int dynamic_tree,

@@ -315,6 +315,39 @@ def zombie_raw(base=(760.0, 100.0, 230.0), spacing=0.2, shells=16, seed=4321):
     return _pack(parts)
 
 
+def zombie_bones(base=(760.0, 100.0, 230.0), pose=1.0, shift=(0.0, 0.0, 0.0)):
+    """Twenty joints (ten bone pairs, zombie.c L110-131 order: head-neck, neck-hip, two arms and two legs in two
+    segments each) for zombie_raw's figure.  Returns (oribones, newbones), float32 [20, 4]: oribones.w = radius of
+    effect of the pair's first joint, newbones.w = twist about the bone (skeleton_vsh.c L113, L137).
+    pose = 0 is the rest pose, larger values bend the limbs further; shift moves the whole figure."""
+    bx, by, bz = base
+    j = dict(
+        head=(bx, by + 158, bz), neck=(bx, by + 132, bz), hip=(bx, by + 78, bz),
+        rshol=(bx - 30, by + 126, bz + 6), relbo=(bx - 30, by + 98, bz + 3), rhand=(bx - 30, by + 70, bz),
+        lshol=(bx + 30, by + 126, bz + 6), lelbo=(bx + 30, by + 98, bz + 3), lhand=(bx + 30, by + 70, bz),
+        rleg=(bx - 12, by + 75, bz), rknee=(bx - 12, by + 38, bz), rfoot=(bx - 12, by + 2, bz),
+        lleg=(bx + 12, by + 75, bz), lknee=(bx + 12, by + 38, bz), lfoot=(bx + 12, by + 2, bz))
+    order = ["head", "neck", "neck", "hip", "rshol", "relbo", "relbo", "rhand", "lshol", "lelbo", "lelbo", "lhand",
+             "rleg", "rknee", "rknee", "rfoot", "lleg", "lknee", "lknee", "lfoot"]
+    effect = dict(head=20.0, neck=30.0, hip=30.0, rshol=12.0, relbo=12.0, rhand=12.0, lshol=12.0, lelbo=12.0,
+                  lhand=12.0, rleg=16.0, rknee=16.0, rfoot=16.0, lleg=16.0, lknee=16.0, lfoot=16.0)
+    ori = np.array([j[k] + (effect[k],) for k in order], dtype=np.float32)
+    p = np.float32(pose)
+    moved = {k: np.array(v, dtype=np.float32) for k, v in j.items()}
+    moved["rhand"] += np.float32([0.0, 6.0, 14.0]) * p      # right forearm swings forward
+    moved["lelbo"] += np.float32([4.0, 0.0, -8.0]) * p      # left arm swings back
+    moved["lhand"] += np.float32([7.0, 3.0, -17.0]) * p
+    moved["rknee"] += np.float32([0.0, 2.0, 12.0]) * p      # right leg steps
+    moved["rfoot"] += np.float32([0.0, 5.0, 6.0]) * p
+    moved["lfoot"] += np.float32([0.0, 3.0, -10.0]) * p
+    moved["head"] += np.float32([3.0, 0.0, 2.0]) * p        # head tilts
+    twist = dict(head=0.15, neck=0.0, hip=0.0, rshol=0.1, relbo=0.2, lshol=0.0, lelbo=-0.1, rleg=0.0, rknee=0.05,
+                 lleg=0.0, lknee=0.0, rhand=0.0, lhand=0.0, rfoot=0.0, lfoot=0.0)
+    sh = np.float32(shift)
+    new = np.array([tuple(moved[k] + sh) + (np.float32(twist[k]) * p,) for k in order], dtype=np.float32)
+    return ori, new
+
+
 def _terrain_height(x, z):
     return (60.0 + 22.0 * np.sin(x / 140.0) * np.cos(z / 170.0) + 6.0 * np.sin(x / 23.0 + z / 31.0)).astype(np.float32)
 

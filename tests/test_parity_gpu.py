@@ -502,6 +502,57 @@ def test_render_with_gpu_built_dynamic_tree(scene_c1):
     rc.destroy()
 
 
+@pytest.mark.parametrize("div", [K.DIV_GLSL, K.DIV_IEEE])
+def test_skinning_pass_equals_the_oracle(div):
+    """octree_cuc_skeleton_update ("next" row 8f #1, first half): the twelve octant digits, the blended normal and
+    the skinned position of every point equal oracle/skeleton_vsh_oracle.c (skeleton_vsh.c L74-226) bit for bit,
+    in both division modes, for the rest pose, two bent poses and a partial model_count."""
+    pos, col, nrm = S.zombie_raw(base=(760.0, 100.0, 230.0), spacing=0.5, shells=3)
+    rc = K.OctreeGlc(b"", device=0)
+    rc.set_division(div)
+    rc.skeleton_alloc_in(pos, nrm)
+    for pose, count in ((0.0, None), (1.0, None), (2.5, None), (1.0, len(pos) // 3), (1.0, 0)):
+        ob, nb = S.zombie_bones(pose=pose, shift=(3.0 * pose, 0.0, -2.0 * pose))
+        n = len(pos) if count is None else count
+        rc.skeleton_update(ob, nb, model_count=count, build_tree=False)
+        digits, nrm_out, pnt_out = rc.skeleton_read_out(n)
+        want_d, want_n, want_p = O.skin(ob, nb, pos[:n], nrm[:n], div=div)
+        assert np.array_equal(digits, want_d), pose
+        assert np.array_equal(nrm_out.view(np.uint32), want_n.view(np.uint32)), pose
+        assert np.array_equal(pnt_out.view(np.uint32), want_p.view(np.uint32)), pose
+        if pose > 0 and n:
+            assert (np.abs(want_p - pos[:n]).max(axis=1) > 1.0).mean() > 0.2   # the pose really moves the figure
+    rc.destroy()
+
+
+def test_skin_build_render_on_the_device_equals_the_host_pipeline(scene_c1):
+    """The reference's per-frame dynamic-model pipeline (qubatron.c L425-452 + L508-548): skin -> read back ->
+    octree_reset + octree_insert_path -> upload tree and normals -> render.  Here all three stages stay on the
+    device; the frame must equal the oracle's frame of the host-side pipeline (oracle skinning, host octree)."""
+    pos, col, nrm = S.zombie_raw(base=(760.0, 100.0, 230.0), spacing=0.6, shells=2)
+    pos, colf, nrm = S.voxelise(pos, col, nrm)
+    rc = K.OctreeGlc(b"", device=0)
+    rc.upload_points(scene_c1.col_s, K.STATIC_COLOR)
+    rc.upload_points(scene_c1.nrm_s, K.STATIC_NORMAL)
+    rc.upload_octree(scene_c1.oct_s)
+    rc.upload_points(colf, K.DYNAMIC_COLOR)
+    rc.skeleton_alloc_in(pos, nrm)
+    for pose in (0.5, 1.5):
+        ob, nb = S.zombie_bones(pose=pose)
+        nodes = rc.skeleton_update(ob, nb, build_tree=True)
+        digits, nrm_out, pnt_out = O.skin(ob, nb, pos, nrm)
+        host = S.HostOctree()
+        host.insert_paths(digits)
+        want = host.nodes()
+        assert nodes == len(want)
+        assert np.array_equal(rc.download_octree(dynamic=True), want)
+        sc = S.Scene("skinned", scene_c1.pnt_s, scene_c1.col_s, scene_c1.nrm_s, scene_c1.oct_s, pnt_out, colf, nrm_out,
+                     want)
+        ref, _ = _render_and_compare(sc, 320, 180, *S.CAMERA_C1, rc=rc)
+        assert (ref["aux"][..., K.AUX_MODEL_D] > 0).sum() > 1000
+    rc.destroy()
+
+
 def test_gpu_voxelise_and_bulk_build_equal_the_host_model():
     """octree_cuc_voxelise_and_build ("next" row 8f #3): the same survivors in the same order as the qmc rules
     (host voxeliser, itself byte-identical to the reference qmc binary in tests/test_host_model.py), the same
