@@ -246,6 +246,15 @@ size_t octree_cuc_build_octree_from_paths(octree_glc_t* rc, const int32_t* oct14
  *   octree_cuc_skeleton_read_out   the buffers the reference reads back every frame (skeleton_glc.c L238-245):
  *                                  oct14 / oct54 / oct94 (int32[4 * n]), normals and skinned points (float[3 * n]),
  *                                  any pointer may be NULL; returns n */
+/*   octree_cuc_skeleton_set_rotations   sin / cos / acos have implementation-defined precision in GLSL ES, so the
+ *                                  ten bone pairs' two rotation quaternions (skeleton_vsh.c L137, L151) are the one
+ *                                  part of the program whose bits depend on the GL driver.  By default the connector
+ *                                  evaluates them once per update on the host with libm (the shader's own TODO,
+ *                                  L72: "rotation quaternions should be precalculated on the CPU per bone").  A host
+ *                                  that has its own values passes them here: float[10][9] = rot_quat xyzw,
+ *                                  axis_quat xyzw, has_axis (0 / 1) per pair; NULL returns to libm.  With a GL
+ *                                  driver's values the outputs equal that driver's bit for bit (tests/golden). */
+void   octree_cuc_skeleton_set_rotations(octree_glc_t* rc, const float* rotations90);
 void   octree_cuc_skeleton_alloc_in(octree_glc_t* rc, const float* pntdata, const float* nrmdata, size_t bytes);
 size_t octree_cuc_skeleton_update(octree_glc_t* rc, const float* oldbones80, const float* newbones80, int model_count,
                                   int maxlevel, float basesize, int build_tree);

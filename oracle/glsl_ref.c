@@ -24,6 +24,7 @@
  *   mode 3 : aux dump of the shadow visibility step(sqr, 15.0)
  *   The aux modes append statements that copy a value to the output; the traversal
  *   and shading code is untouched.
+ *   mode 20 / 21 : skeleton_vsh.c through transform feedback (see skin_main below)
  * prints one JSON line with renderer, version and per-frame seconds.
  */
 #define _GNU_SOURCE
@@ -37,6 +38,8 @@
 
 extern const char _binary_octree_fsh_c_start[], _binary_octree_fsh_c_end[];
 extern const char _binary_octree_vsh_c_start[], _binary_octree_vsh_c_end[];
+extern const char _binary_skeleton_vsh_c_start[], _binary_skeleton_vsh_c_end[];
+extern const char _binary_skeleton_fsh_c_start[], _binary_skeleton_fsh_c_end[];
 
 #ifndef MESA_DIR
     #define MESA_DIR "/opt/nvidia/nsight-compute/2025.2.1/host/linux-desktop-glibc_2_11_3-x64/Mesa"
@@ -78,6 +81,12 @@ typedef long         GLsizeiptr;
 #define GL_RENDERER 0x1F01
 #define GL_VERSION 0x1F02
 #define GL_PACK_ALIGNMENT 0x0D05
+#define GL_POINTS 0
+#define GL_STATIC_DRAW 0x88E4
+#define GL_STREAM_READ 0x88E1
+#define GL_RASTERIZER_DISCARD 0x8C89
+#define GL_TRANSFORM_FEEDBACK_BUFFER 0x8C8E
+#define GL_SEPARATE_ATTRIBS 0x8C8D
 #define GL_UNPACK_ALIGNMENT 0x0CF5
 
 #define GLX_RGBA 4
@@ -134,6 +143,11 @@ GLFN(const unsigned char*, glGetString, GLenum)
 GLFN(GLenum, glGetError, void)
 GLFN(void, glEnable, GLenum)
 GLFN(void, glPixelStorei, GLenum, GLint)
+GLFN(void, glTransformFeedbackVaryings, GLuint, GLsizei, const GLchar* const*, GLenum)
+GLFN(void, glBindBufferBase, GLenum, GLuint, GLuint)
+GLFN(void, glBeginTransformFeedback, GLenum)
+GLFN(void, glEndTransformFeedback, void)
+GLFN(void, glGetBufferSubData, GLenum, long, GLsizeiptr, void*)
 
 static void die(const char* m)
 {
@@ -213,34 +227,8 @@ static GLuint data_texture(int unit, const void* data, size_t texels, int is_int
     return t;
 }
 
-int main(int argc, char** argv)
+static void gl_context(void)
 {
-    if (argc < 3) die("usage: glsl_ref in.bin out.rgba [mode] [repeat]");
-    int mode   = argc > 3 ? atoi(argv[3]) : 0;
-    int repeat = argc > 4 ? atoi(argv[4]) : 1;
-
-    /* ---- input ---- */
-    FILE* f = fopen(argv[1], "rb");
-    if (!f) die("cannot open input");
-    int64_t hdr[8];
-    float   u[16];
-    if (fread(hdr, 8, 8, f) != 8 || fread(u, 4, 16, f) != 16) die("short input header");
-    int64_t nodes_s = hdr[0], nodes_d = hdr[1], pts_s = hdr[2], pts_d = hdr[3];
-    int     W = (int) hdr[4], H = (int) hdr[5], maxlevel = (int) hdr[6], shoot = (int) hdr[7];
-    /* u: camfp[0..2] angle[3..5] light[6..8] basecube[9..12] dims[13..14] */
-    int32_t* oct_s = malloc((size_t) (nodes_s ? nodes_s : 1) * 48);
-    int32_t* oct_d = malloc((size_t) (nodes_d ? nodes_d : 1) * 48);
-    float*   col_s = malloc((size_t) (pts_s ? pts_s : 1) * 12);
-    float*   nrm_s = malloc((size_t) (pts_s ? pts_s : 1) * 12);
-    float*   col_d = malloc((size_t) (pts_d ? pts_d : 1) * 12);
-    float*   nrm_d = malloc((size_t) (pts_d ? pts_d : 1) * 12);
-    if (fread(oct_s, 48, nodes_s, f) != (size_t) nodes_s || fread(oct_d, 48, nodes_d, f) != (size_t) nodes_d ||
-        fread(col_s, 12, pts_s, f) != (size_t) pts_s || fread(nrm_s, 12, pts_s, f) != (size_t) pts_s ||
-        fread(col_d, 12, pts_d, f) != (size_t) pts_d || fread(nrm_d, 12, pts_d, f) != (size_t) pts_d)
-        die("short input body");
-    fclose(f);
-    if (W > 2048 || H > 2048) die("the reference's render target is 2048x2048 (octree_glc.c L237)");
-
     /* ---- GL via the stubbed X11 + Mesa llvmpipe ---- */
     char  path[4096];
     char* self = realpath("/proc/self/exe", NULL);
@@ -280,7 +268,179 @@ int main(int argc, char** argv)
     LOAD(glFramebufferTexture2D) LOAD(glCheckFramebufferStatus) LOAD(glViewport) LOAD(glClearColor) LOAD(glClear)
     LOAD(glGenBuffers) LOAD(glBindBuffer) LOAD(glBufferData) LOAD(glGenVertexArrays) LOAD(glBindVertexArray)
     LOAD(glEnableVertexAttribArray) LOAD(glVertexAttribPointer) LOAD(glDrawArrays) LOAD(glFinish) LOAD(glReadPixels)
-    LOAD(glGetString) LOAD(glGetError) LOAD(glEnable) LOAD(glPixelStorei)
+    LOAD(glGetString) LOAD(glGetError) LOAD(glEnable) LOAD(glPixelStorei) LOAD(glTransformFeedbackVaryings)
+    LOAD(glBindBufferBase) LOAD(glBeginTransformFeedback) LOAD(glEndTransformFeedback) LOAD(glGetBufferSubData)
+}
+
+static char* embedded(const char* b, const char* e)
+{
+    size_t n = (size_t) (e - b);
+    char*  t = malloc(n + 1);
+    memcpy(t, b, n);
+    t[n] = 0;
+    return t;
+}
+
+/*
+ * mode 20 / 21: the reference's skinning vertex program skeleton_vsh.c through transform feedback, restating the
+ * host side of /root/reference/src/qubatron/skeleton_glc.c L77-137 (program, varyings, VAO), L222-251 (uniforms,
+ * the GL_POINTS draw with rasterizer discard) and L257-300 (buffers).
+ *   in.bin : int64 hdr[2] = {n, maxlevel}; float basesize, pad; float oldbones[80], newbones[80];
+ *            float positions[3n], normals[3n]
+ *   out    : int32 oct14[4n], oct54[4n], oct94[4n]; float normal_out[3n]
+ *   mode 20: the shader exactly as shipped
+ *   mode 21: main()'s `pnt` captured in place of normal_out
+ *   mode 22: oldbone_rot_quat, bonesangle_rot_quat and (bone, has_axis) of bone pair $QB_SKIN_BONE in place of the
+ *            three digit vectors -- the only driver-dependent values of the program (sin / cos / acos)
+ */
+static int skin_main(const char* in, const char* outp, int mode, int repeat)
+{
+    FILE* f = fopen(in, "rb");
+    if (!f) die("cannot open input");
+    int64_t hdr[2];
+    float   fb[2], ob[80], nb[80];
+    if (fread(hdr, 8, 2, f) != 2 || fread(fb, 4, 2, f) != 2 || fread(ob, 4, 80, f) != 80 || fread(nb, 4, 80, f) != 80)
+        die("short skin input header");
+    size_t n   = (size_t) hdr[0];
+    float* pos = malloc((n ? n : 1) * 12);
+    float* nrm = malloc((n ? n : 1) * 12);
+    if (fread(pos, 12, n, f) != n || fread(nrm, 12, n, f) != n) die("short skin input body");
+    fclose(f);
+
+    gl_context();
+    char* vsh = embedded(_binary_skeleton_vsh_c_start, _binary_skeleton_vsh_c_end);
+    char* fsh = embedded(_binary_skeleton_fsh_c_start, _binary_skeleton_fsh_c_end);
+    const GLchar* vary[4] = {"oct14", "oct54", "oct94", "normal_out"}; /* skeleton_glc.c L99-100 */
+    if (mode == 21) /* `pnt` captured in place of normal_out (llvmpipe allows 4 separate varyings) */
+    {
+        vsh     = patch(vsh, "flat out vec3  normal_out;", "flat out vec3  normal_out;\nflat out vec3 qb_pnt;");
+        vsh     = patch(vsh, "    vec4 cube = basecube;", "    qb_pnt = pnt;\n    vec4 cube = basecube;");
+        vary[3] = "qb_pnt";
+    }
+    if (mode == 22) /* the two rotation quaternions of bone pair QB_SKIN_BONE, as this GL evaluates them */
+    {
+        char buf[512];
+        int  bone = getenv("QB_SKIN_BONE") ? atoi(getenv("QB_SKIN_BONE")) : 0;
+        vsh = patch(vsh, "flat out vec3  normal_out;",
+                    "flat out vec3  normal_out;\nflat out vec4 qb_rq;\nflat out vec4 qb_aq;\nflat out ivec4 qb_id;");
+        vsh = patch(vsh, "    vec3  corner_points[POINT_COUNT];",
+                    "    qb_rq = vec4(0.0); qb_aq = vec4(0.0); qb_id = ivec4(-1, 0, 0, 0);\n"
+                    "    vec3  corner_points[POINT_COUNT];");
+        snprintf(buf, sizeof(buf),
+                 "vec4 oldbone_rot_quat = quat_from_axis_angle(oldbone_norm, newbones[i].w);\n"
+                 "if (i == %d) { qb_rq = oldbone_rot_quat; qb_id.x = i; }", bone);
+        vsh = patch(vsh, "vec4 oldbone_rot_quat = quat_from_axis_angle(oldbone_norm, newbones[i].w);", buf);
+        snprintf(buf, sizeof(buf),
+                 "vec4 bonesangle_rot_quat = quat_from_axis_angle(normalize(bones_axis), bones_angle);\n"
+                 "if (i == %d) { qb_aq = bonesangle_rot_quat; qb_id.y = 1; }", bone);
+        vsh = patch(vsh, "vec4 bonesangle_rot_quat = quat_from_axis_angle(normalize(bones_axis), bones_angle);", buf);
+        vary[0] = "qb_rq", vary[1] = "qb_aq", vary[2] = "qb_id";
+    }
+    GLuint prog = glCreateProgram();
+    glAttachShader(prog, compile(GL_VERTEX_SHADER, vsh));
+    glAttachShader(prog, compile(GL_FRAGMENT_SHADER, fsh));
+    const int nvary = 4;
+    glTransformFeedbackVaryings(prog, nvary, vary, GL_SEPARATE_ATTRIBS);
+    glBindAttribLocation(prog, 0, "position");
+    glBindAttribLocation(prog, 1, "normal");
+    glLinkProgram(prog);
+    GLint ok = 0;
+    glGetProgramiv(prog, GL_LINK_STATUS, &ok);
+    if (!ok)
+    {
+        char log[4096];
+        glGetProgramInfoLog(prog, sizeof(log), NULL, log);
+        fprintf(stderr, "glsl_ref: link failed:\n%s\n", log);
+        return 2;
+    }
+
+    GLuint vin[2], vao, vout[4];
+    glGenBuffers(2, vin);
+    glGenVertexArrays(1, &vao);
+    glBindVertexArray(vao);
+    glBindBuffer(GL_ARRAY_BUFFER, vin[0]);
+    glBufferData(GL_ARRAY_BUFFER, (GLsizeiptr) (n * 12), pos, GL_STATIC_DRAW);
+    glEnableVertexAttribArray(0);
+    glVertexAttribPointer(0, 3, GL_FLOAT, 0, sizeof(GLfloat) * 3, 0);
+    glBindBuffer(GL_ARRAY_BUFFER, vin[1]);
+    glBufferData(GL_ARRAY_BUFFER, (GLsizeiptr) (n * 12), nrm, GL_STATIC_DRAW);
+    glEnableVertexAttribArray(1);
+    glVertexAttribPointer(1, 3, GL_FLOAT, 0, sizeof(GLfloat) * 3, 0);
+    const size_t osz[4] = {n * 16, n * 16, n * 16, n * 12};
+    glGenBuffers(4, vout);
+    for (int i = 0; i < nvary; i++)
+    {
+        glBindBuffer(GL_ARRAY_BUFFER, vout[i]);
+        glBufferData(GL_ARRAY_BUFFER, (GLsizeiptr) (osz[i] ? osz[i] : 16), NULL, GL_STREAM_READ);
+    }
+    glBindBuffer(GL_ARRAY_BUFFER, 0);
+
+    glEnable(GL_RASTERIZER_DISCARD);
+    glUseProgram(prog);
+    GLfloat basecube[4] = {0.0f, fb[0], fb[0], fb[0]};
+    glUniform4fv(glGetUniformLocation(prog, "oldbones"), 20, ob);
+    glUniform4fv(glGetUniformLocation(prog, "newbones"), 20, nb);
+    glUniform4fv(glGetUniformLocation(prog, "basecube"), 1, basecube);
+    glUniform1i(glGetUniformLocation(prog, "maxlevel"), (GLint) hdr[1]);
+    for (int i = 0; i < nvary; i++) glBindBufferBase(GL_TRANSFORM_FEEDBACK_BUFFER, (GLuint) i, vout[i]);
+
+    printf("{\"renderer\": \"%s\", \"version\": \"%s\", \"mode\": %d, \"frame_s\": [", glGetString(GL_RENDERER),
+           glGetString(GL_VERSION), mode);
+    for (int r = 0; r < repeat; r++)
+    {
+        double t0 = now();
+        glBeginTransformFeedback(GL_POINTS);
+        glDrawArrays(GL_POINTS, 0, (GLsizei) n);
+        glEndTransformFeedback();
+        glFinish();
+        printf("%s%.6f", r ? ", " : "", now() - t0);
+    }
+    printf("], \"gl_error\": %u}\n", glGetError());
+
+    f = fopen(outp, "wb");
+    if (!f) die("cannot open output");
+    for (int i = 0; i < nvary; i++)
+    {
+        void* host = malloc(osz[i] ? osz[i] : 16);
+        glBindBuffer(GL_TRANSFORM_FEEDBACK_BUFFER, vout[i]);
+        glGetBufferSubData(GL_TRANSFORM_FEEDBACK_BUFFER, 0, (GLsizeiptr) osz[i], host);
+        fwrite(host, 1, osz[i], f);
+        free(host);
+    }
+    fclose(f);
+    return 0;
+}
+
+int main(int argc, char** argv)
+{
+    if (argc < 3) die("usage: glsl_ref in.bin out.rgba [mode] [repeat]");
+    int mode   = argc > 3 ? atoi(argv[3]) : 0;
+    int repeat = argc > 4 ? atoi(argv[4]) : 1;
+    if (mode >= 20 && mode <= 22) return skin_main(argv[1], argv[2], mode, repeat);
+
+    /* ---- input ---- */
+    FILE* f = fopen(argv[1], "rb");
+    if (!f) die("cannot open input");
+    int64_t hdr[8];
+    float   u[16];
+    if (fread(hdr, 8, 8, f) != 8 || fread(u, 4, 16, f) != 16) die("short input header");
+    int64_t nodes_s = hdr[0], nodes_d = hdr[1], pts_s = hdr[2], pts_d = hdr[3];
+    int     W = (int) hdr[4], H = (int) hdr[5], maxlevel = (int) hdr[6], shoot = (int) hdr[7];
+    /* u: camfp[0..2] angle[3..5] light[6..8] basecube[9..12] dims[13..14] */
+    int32_t* oct_s = malloc((size_t) (nodes_s ? nodes_s : 1) * 48);
+    int32_t* oct_d = malloc((size_t) (nodes_d ? nodes_d : 1) * 48);
+    float*   col_s = malloc((size_t) (pts_s ? pts_s : 1) * 12);
+    float*   nrm_s = malloc((size_t) (pts_s ? pts_s : 1) * 12);
+    float*   col_d = malloc((size_t) (pts_d ? pts_d : 1) * 12);
+    float*   nrm_d = malloc((size_t) (pts_d ? pts_d : 1) * 12);
+    if (fread(oct_s, 48, nodes_s, f) != (size_t) nodes_s || fread(oct_d, 48, nodes_d, f) != (size_t) nodes_d ||
+        fread(col_s, 12, pts_s, f) != (size_t) pts_s || fread(nrm_s, 12, pts_s, f) != (size_t) pts_s ||
+        fread(col_d, 12, pts_d, f) != (size_t) pts_d || fread(nrm_d, 12, pts_d, f) != (size_t) pts_d)
+        die("short input body");
+    fclose(f);
+    if (W > 2048 || H > 2048) die("the reference's render target is 2048x2048 (octree_glc.c L237)");
+
+    gl_context();
 
     /* ---- shaders: the reference text, byte for byte (mode 0) ---- */
     size_t fl  = (size_t) (_binary_octree_fsh_c_end - _binary_octree_fsh_c_start);

@@ -73,8 +73,9 @@ def lib(div=DIV_GLSL):
         l.qb_oracle_trace_batch.argtypes = [C.POINTER(_Scene), C.POINTER(Uniforms), C.c_int64, C.c_void_p, C.c_void_p,
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         l.qb_oracle_pixel_ray.argtypes = [C.POINTER(Uniforms), C.c_int, C.c_int, C.c_void_p]
-        l.qb_oracle_skin.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p,
-                                     C.c_void_p, C.c_void_p, C.c_void_p]
+        l.qb_oracle_skin_rot.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        l.qb_oracle_bone_rotations.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _libs[div] = l
     return _libs[div]
 
@@ -139,19 +140,30 @@ def trace_batch(oscene, u, pos, direction, threads=0, div=DIV_GLSL):
     return result, nodes, models, isp
 
 
-def skin(oldbones, newbones, positions, normals, maxlevel=12, basesize=1800.0, div=DIV_GLSL):
-    """skeleton_vsh.c main() for n points: (digits int32[n,12], normal_out f32[n,3], skinned point f32[n,3])."""
+def bone_rotations(oldbones, newbones, div=DIV_GLSL):
+    """float32 [10, 9]: rot_quat, axis_quat, has_axis per bone pair, evaluated with libm."""
+    ob = np.ascontiguousarray(oldbones, dtype=np.float32).reshape(20, 4)
+    nb = np.ascontiguousarray(newbones, dtype=np.float32).reshape(20, 4)
+    out = np.zeros((10, 9), dtype=np.float32)
+    lib(div).qb_oracle_bone_rotations(_ptr(ob), _ptr(nb), _ptr(out))
+    return out
+
+
+def skin(oldbones, newbones, positions, normals, maxlevel=12, basesize=1800.0, div=DIV_GLSL, rotations=None):
+    """skeleton_vsh.c main() for n points: (digits int32[n,12], normal_out f32[n,3], skinned point f32[n,3]).
+    rotations: optional float32 [10, 9] per-bone rotations replacing the libm ones (see bone_rotations)."""
     ob = np.ascontiguousarray(oldbones, dtype=np.float32).reshape(20, 4)
     nb = np.ascontiguousarray(newbones, dtype=np.float32).reshape(20, 4)
     pos = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
     nrm = np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 3)
+    rot = None if rotations is None else np.ascontiguousarray(rotations, dtype=np.float32).reshape(10, 9)
     n = len(pos)
     cube = np.array([0.0, basesize, basesize, basesize], dtype=np.float32)
     digits = np.zeros((n, 12), dtype=np.int32)
     nout = np.zeros((n, 3), dtype=np.float32)
     pout = np.zeros((n, 3), dtype=np.float32)
-    lib(div).qb_oracle_skin(_ptr(ob), _ptr(nb), _ptr(cube), int(maxlevel), n, _ptr(pos), _ptr(nrm), _ptr(digits),
-                            _ptr(nout), _ptr(pout))
+    lib(div).qb_oracle_skin_rot(_ptr(ob), _ptr(nb), None if rot is None else _ptr(rot), _ptr(cube), int(maxlevel), n,
+                                _ptr(pos), _ptr(nrm), _ptr(digits), _ptr(nout), _ptr(pout))
     return digits, nout, pout
 
 
@@ -298,3 +310,73 @@ def glsl_render(scene, u, mode=0, repeat=1, threads=None, workdir=None):
     if mode != 0:
         out = out.view(np.int32).reshape(H, W)
     return out, info
+
+
+def _glsl_skin_run(mode, ob, nb, pos, nrm, maxlevel, basesize, repeat=1, workdir=None, env=None):
+    import json
+    import tempfile
+    n = len(pos)
+    with tempfile.TemporaryDirectory(dir=workdir) as d:
+        fin, fout = os.path.join(d, "in.bin"), os.path.join(d, "out.bin")
+        with open(fin, "wb") as f:
+            f.write(np.array([n, maxlevel], dtype=np.int64).tobytes())
+            f.write(np.array([basesize, 0.0], dtype=np.float32).tobytes())
+            for a in (ob, nb, pos, nrm):
+                f.write(a.tobytes())
+        e = dict(os.environ)
+        e.update(env or {})
+        r = subprocess.run([REF_GLSL, fin, fout, str(mode), str(repeat)], stdout=subprocess.PIPE,
+                           stderr=subprocess.PIPE, text=True, env=e)
+        if r.returncode != 0:
+            raise RuntimeError("glsl_ref failed (%d): %s" % (r.returncode, r.stderr[-2000:]))
+        info = json.loads(r.stdout.strip().splitlines()[-1])
+        if info["gl_error"]:
+            raise RuntimeError("glsl_ref: GL error %d" % info["gl_error"])
+        raw = np.fromfile(fout, dtype=np.uint8)
+    o = n * 16
+    return [raw[k * o:(k + 1) * o] for k in range(3)] + [raw[3 * o:3 * o + n * 12]], info
+
+
+def _skin_args(oldbones, newbones, positions, normals):
+    return (np.ascontiguousarray(oldbones, dtype=np.float32).reshape(20, 4),
+            np.ascontiguousarray(newbones, dtype=np.float32).reshape(20, 4),
+            np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3),
+            np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 3))
+
+
+def glsl_skin(oldbones, newbones, positions, normals, maxlevel=12, basesize=1800.0, points=False, repeat=1,
+              workdir=None):
+    """Run the reference's skinning vertex program (skeleton_vsh.c) through transform feedback on llvmpipe.
+    Returns (digits int32 [n,12], normal_out f32 [n,3], info) with the shader exactly as shipped (glsl_ref mode 20);
+    points=True captures main()'s `pnt` in place of normal_out (mode 21, one statement added)."""
+    ob, nb, pos, nrm = _skin_args(oldbones, newbones, positions, normals)
+    n = len(pos)
+    bufs, info = _glsl_skin_run(21 if points else 20, ob, nb, pos, nrm, maxlevel, basesize, repeat, workdir)
+    digits = np.concatenate([b.view(np.int32).reshape(n, 4) for b in bufs[:3]], axis=1)
+    return digits, bufs[3].view(np.float32).reshape(n, 3).copy(), info
+
+
+def glsl_bone_rotations(oldbones, newbones, positions, normals, workdir=None):
+    """The per-bone rotations as the GL driver evaluates them (sin / cos / acos are implementation-defined):
+    glsl_ref mode 22 captures oldbone_rot_quat / bonesangle_rot_quat of ONE chosen bone pair per run.  Returns
+    float32 [10, 9] in bone_rotations' layout and a bool [10] mask of the pairs that had any point in range (the
+    others never contribute)."""
+    ob, nb, pos, nrm = _skin_args(oldbones, newbones, positions, normals)
+    n = len(pos)
+    out = np.zeros((10, 9), dtype=np.float32)
+    seen = np.zeros(10, dtype=bool)
+    for k in range(10):
+        bufs, _ = _glsl_skin_run(22, ob, nb, pos, nrm, 12, 1800.0, workdir=workdir, env={"QB_SKIN_BONE": str(2 * k)})
+        rq = bufs[0].view(np.float32).reshape(n, 4)
+        aq = bufs[1].view(np.float32).reshape(n, 4)
+        ident = bufs[2].view(np.int32).reshape(n, 4)
+        hit = np.nonzero(ident[:, 0] == 2 * k)[0]
+        if len(hit):
+            j = hit[0]
+            assert (rq[hit].view(np.uint32) == rq[j].view(np.uint32)).all()     # per-bone, not per-point
+            assert (aq[hit].view(np.uint32) == aq[j].view(np.uint32)).all()
+            seen[k] = True
+            out[k, 0:4] = rq[j]
+            out[k, 4:8] = aq[j]
+            out[k, 8] = float(ident[j, 1])
+    return out, seen

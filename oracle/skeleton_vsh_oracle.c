@@ -10,11 +10,14 @@
  *     L188-226 main: 12 octant digits of the skinned point
  * with the uniforms of skeleton_glc.c L222-227 (oldbones / newbones: 20 x vec4, basecube, maxlevel).
  *
- * "next" row SURVEY 8f #1.  Parity status: this restatement is what the CUDA kernel is checked against bit for
- * bit; it has NOT been run against the shader on llvmpipe (transform feedback is not wired into oracle/glsl_ref.c),
- * so for this row parity is pinned to the restatement only.  Everything that involves sin / cos / acos depends on
- * the bones alone (the shader's own TODO, L72: "rotation quaternions should be precalculated on the CPU per
- * bone"), is evaluated with libm per bone pair, and the per-point arithmetic is + - * / sqrt only.
+ * "next" row SURVEY 8f #1.  Parity status: PINNED against the shader itself.  oracle/glsl_ref.c (modes 20-22) runs
+ * skeleton_vsh.c unmodified through transform feedback on Mesa llvmpipe; tests/golden/skin_*.npz hold its outputs
+ * and tests/test_golden.py checks this restatement against them bit for bit (digits, normals, skinned positions).
+ * sin / cos / acos have implementation-defined precision in GLSL ES and are used only for the two rotation
+ * quaternions of each bone pair, which depend on the bones alone (the shader's own TODO, L72: "rotation
+ * quaternions should be precalculated on the CPU per bone"): the fixtures record the driver's 10 x 2 quaternions,
+ * qb_oracle_skin_rot takes them as an input, and without them they are evaluated with libm.  The per-point
+ * arithmetic is + - * / sqrt only.
  *
  * Built into both oracle libraries (IEEE `/` and, with -DQB_DIV_MUL_RCP, Mesa's a * (1/b) lowering).
  */
@@ -198,12 +201,50 @@ static void skin_point(const qb_bone_consts* bc, s3 position, s3 normal, const f
 
 /* n points: positions / normals float[3n] -> digits int32[12n] (oct14 | oct54 | oct94 per point), normals
  * float[3n], skinned positions float[3n] (optional) */
+/* The ten bone pairs' rotations as 9 floats each: rot_quat[4], axis_quat[4], has_axis (0 / 1).  sin, cos and acos
+ * have implementation-defined precision in GLSL ES (spec 4.5.1), so these 90 numbers are the one part of the shader
+ * whose bits depend on the GL driver; everything downstream of them is + - * / sqrt. */
+void qb_oracle_bone_rotations(const float* oldbones80, const float* newbones80, float* out90)
+{
+    qb_bone_consts bc[10];
+    qb_oracle_bone_consts(oldbones80, newbones80, bc);
+    for (int k = 0; k < 10; k++)
+    {
+        float* o = out90 + k * 9;
+        o[0] = bc[k].rot_quat.x, o[1] = bc[k].rot_quat.y, o[2] = bc[k].rot_quat.z, o[3] = bc[k].rot_quat.w;
+        o[4] = bc[k].axis_quat.x, o[5] = bc[k].axis_quat.y, o[6] = bc[k].axis_quat.z, o[7] = bc[k].axis_quat.w;
+        o[8] = (float) bc[k].has_axis;
+    }
+}
+
+void qb_oracle_skin_rot(const float* oldbones80, const float* newbones80, const float* rotations90,
+                        const float basecube[4], int maxlevel, int64_t n, const float* positions,
+                        const float* normals, int32_t* digits12, float* normals_out, float* points_out);
+
 void qb_oracle_skin(const float* oldbones80, const float* newbones80, const float basecube[4], int maxlevel,
                     int64_t n, const float* positions, const float* normals, int32_t* digits12, float* normals_out,
                     float* points_out)
 {
+    qb_oracle_skin_rot(oldbones80, newbones80, NULL, basecube, maxlevel, n, positions, normals, digits12, normals_out,
+                       points_out);
+}
+
+/* rotations90 != NULL: use these per-bone rotations (e.g. the ones a GL driver produced, oracle/glsl_ref.c mode 22)
+ * instead of the libm ones */
+void qb_oracle_skin_rot(const float* oldbones80, const float* newbones80, const float* rotations90,
+                        const float basecube[4], int maxlevel, int64_t n, const float* positions,
+                        const float* normals, int32_t* digits12, float* normals_out, float* points_out)
+{
     qb_bone_consts bc[10];
     qb_oracle_bone_consts(oldbones80, newbones80, bc);
+    if (rotations90)
+        for (int k = 0; k < 10; k++)
+        {
+            const float* o   = rotations90 + k * 9;
+            bc[k].rot_quat   = (s4){o[0], o[1], o[2], o[3]};
+            bc[k].axis_quat  = (s4){o[4], o[5], o[6], o[7]};
+            bc[k].has_axis   = o[8] != 0.0f;
+        }
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < n; i++)
     {

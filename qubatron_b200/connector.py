@@ -84,6 +84,7 @@ _PROTOS = {
     "octree_cuc_build_octree_from_paths": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_void_p, C.c_void_p, C.c_void_p,
                                                         C.c_size_t, C.c_int, C.c_int, C.c_int]),
     "octree_cuc_skeleton_alloc_in": (None, [C.POINTER(octree_glc_t), C.c_void_p, C.c_void_p, C.c_size_t]),
+    "octree_cuc_skeleton_set_rotations": (None, [C.POINTER(octree_glc_t), C.c_void_p]),
     "octree_cuc_skeleton_update": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                                 C.c_float, C.c_int]),
     "octree_cuc_skeleton_read_out": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_void_p, C.c_void_p, C.c_void_p,
@@ -325,6 +326,13 @@ class OctreeGlc:
         return int(self.lib.octree_cuc_skeleton_update(self._p, ob.ctypes.data_as(C.c_void_p),
                                                        nb.ctypes.data_as(C.c_void_p), n, int(maxlevel),
                                                        float(basesize), int(bool(build_tree))))
+
+    def skeleton_set_rotations(self, rotations):
+        if rotations is None:
+            self.lib.octree_cuc_skeleton_set_rotations(self._p, None)
+        else:
+            r = np.ascontiguousarray(rotations, dtype=np.float32).reshape(10, 9)
+            self.lib.octree_cuc_skeleton_set_rotations(self._p, r.ctypes.data_as(C.c_void_p))
 
     def skeleton_read_out(self, n):
         p14, p54, p94 = (np.zeros((n, 4), np.int32) for _ in range(3))

@@ -270,6 +270,8 @@ struct Impl
     int4 * skin_p14 = nullptr, *skin_p54 = nullptr, *skin_p94 = nullptr;
     float* skin_pnt_out = nullptr;
     size_t skin_count   = 0; // points of the last update
+    bool   skin_rot_set = false; // per-bone rotations supplied by the host instead of libm
+    float  skin_rot[90];
 
     uint64_t launches = 0;
     uint64_t memsize  = 0;
@@ -1571,6 +1573,14 @@ size_t octree_cuc_skeleton_update(octree_glc_t* rc, const float* oldbones80, con
     flush_pending(I);
     SkinParams S;
     bone_consts(oldbones80, newbones80, I->div_mode, S.bones);
+    if (I->skin_rot_set)
+        for (int k = 0; k < 10; k++)
+        {
+            const float* o = I->skin_rot + k * 9;
+            memcpy(S.bones[k].rot_quat, o, 16);
+            memcpy(S.bones[k].axis_quat, o + 4, 16);
+            S.bones[k].has_axis = o[8] != 0.0f;
+        }
     S.basesize = basesize;
     S.maxlevel = maxlevel;
     const size_t n = (size_t) model_count;
@@ -1594,6 +1604,13 @@ size_t octree_cuc_skeleton_update(octree_glc_t* rc, const float* oldbones80, con
                                         (const int*) I->skin_p54, (const int*) I->skin_p94, n, 0, maxlevel);
     publish_memsize(rc, I);
     return nodes;
+}
+
+void octree_cuc_skeleton_set_rotations(octree_glc_t* rc, const float* rotations90)
+{
+    Impl* I         = impl_of(rc);
+    I->skin_rot_set = rotations90 != nullptr;
+    if (rotations90) memcpy(I->skin_rot, rotations90, sizeof(I->skin_rot));
 }
 
 size_t octree_cuc_skeleton_read_out(octree_glc_t* rc, int32_t* oct14, int32_t* oct54, int32_t* oct94, float* nrm_out,

@@ -36,3 +36,12 @@ def load(name):
         if scene_hash(sc) != str(g["scene_sha256"]):
             return None, args, g
     return sc, args, g
+
+
+SKIN_CASES = ["skin_rest", "skin_walk", "skin_bent"]
+
+
+def load_skin(name):
+    """(positions, normals, golden dict) of a skinning fixture (tests/golden/make_golden_skin.py)."""
+    i = np.load(os.path.join(GOLDEN, "skin_inputs.npz"))
+    return i["positions"], i["normals"], np.load(os.path.join(GOLDEN, name + ".npz"))

@@ -36,3 +36,22 @@ def test_ieee_oracle_is_within_a_few_pixels_of_the_shader(name):
     r = O.render(O.OracleScene(sc), O.uniforms(**args), div=O.DIV_IEEE)
     differing = int((r["rgba"] != g["rgba"]).any(axis=-1).sum())
     assert differing <= 4, differing
+
+
+@pytest.mark.parametrize("name", golden_util.SKIN_CASES)
+def test_skin_oracle_equals_the_reference_vertex_program(name):
+    """oracle/skeleton_vsh_oracle.c against skeleton_vsh.c as llvmpipe ran it through transform feedback: with the
+    driver's own ten bone rotations (sin / cos / acos are implementation-defined) every digit, normal and skinned
+    position is bit-identical; with libm rotations the residual is the driver's acos polynomial (< 0.01 units)."""
+    pos, nrm, g = golden_util.load_skin(name)
+    d, no, pnt = O.skin(g["oldbones"], g["newbones"], pos, nrm, rotations=g["rotations"])
+    assert np.array_equal(d, g["digits"])
+    assert np.array_equal(no.view(np.uint32), g["normal_out"].view(np.uint32))
+    assert np.array_equal(pnt.view(np.uint32), g["pnt"].view(np.uint32))
+    libm = O.bone_rotations(g["oldbones"], g["newbones"])
+    assert np.abs(libm - g["rotations"]).max() < 1e-4
+    d2, no2, pnt2 = O.skin(g["oldbones"], g["newbones"], pos, nrm)
+    assert np.abs(pnt2 - g["pnt"]).max() < 1e-2 and np.abs(no2 - g["normal_out"]).max() < 1e-3
+    assert (d2 != g["digits"]).any(axis=1).mean() < 0.01
+    if name == "skin_rest":
+        assert np.array_equal(d2, g["digits"]) and np.array_equal(pnt2.view(np.uint32), g["pnt"].view(np.uint32))

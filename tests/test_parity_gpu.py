@@ -525,6 +525,28 @@ def test_skinning_pass_equals_the_oracle(div):
     rc.destroy()
 
 
+@pytest.mark.parametrize("name", __import__("golden_util").SKIN_CASES)
+def test_skinning_pass_equals_the_reference_vertex_program_on_llvmpipe(name):
+    """The CUDA skinning pass against skeleton_vsh.c itself (tests/golden/skin_*.npz, transform feedback on
+    llvmpipe): given the driver's ten bone rotations, every digit, normal and skinned position is bit-identical."""
+    import golden_util
+    pos, nrm, g = golden_util.load_skin(name)
+    rc = K.OctreeGlc(b"", device=0)
+    rc.skeleton_alloc_in(pos, nrm)
+    rc.skeleton_set_rotations(g["rotations"])
+    rc.skeleton_update(g["oldbones"], g["newbones"], build_tree=False)
+    digits, nrm_out, pnt_out = rc.skeleton_read_out(len(pos))
+    assert np.array_equal(digits, g["digits"])
+    assert np.array_equal(nrm_out.view(np.uint32), g["normal_out"].view(np.uint32))
+    assert np.array_equal(pnt_out.view(np.uint32), g["pnt"].view(np.uint32))
+    rc.skeleton_set_rotations(None)   # back to libm: equals the oracle with libm rotations
+    rc.skeleton_update(g["oldbones"], g["newbones"], build_tree=False)
+    digits, nrm_out, pnt_out = rc.skeleton_read_out(len(pos))
+    want_d, want_n, want_p = O.skin(g["oldbones"], g["newbones"], pos, nrm)
+    assert np.array_equal(digits, want_d) and np.array_equal(pnt_out.view(np.uint32), want_p.view(np.uint32))
+    rc.destroy()
+
+
 def test_skin_build_render_on_the_device_equals_the_host_pipeline(scene_c1):
     """The reference's per-frame dynamic-model pipeline (qubatron.c L425-452 + L508-548): skin -> read back ->
     octree_reset + octree_insert_path -> upload tree and normals -> render.  Here all three stages stay on the
