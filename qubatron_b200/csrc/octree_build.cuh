@@ -10,76 +10,122 @@
 // distinct path prefix, its creator is the smallest point index having that
 // prefix, and node indices follow the order (creator, level).
 //
-// Parallel form:
-//   1. level by level, every point proposes itself for the slot (its node at this
-//      level, its digit) with atomicMin; occupied slots become the next level's
-//      nodes under temporary ids (scan), and every point steps into its child;
-//   2. temporary nodes are sorted by (creator, level) -- one radix sort -- which
-//      yields the reference's indices;
-//   3. children are renumbered and written straight into the traversal layout
-//      (octree_types.cuh: index + child-exists mask nibbles, model array).
-// No host round trip: the paths may already live on the device.
+// Parallel form (v2, sort based -- the first version walked all points down the tree level by level with one
+// atomicMin per point and level, which spent 2.1 of its 3.4 ms on contended atomics):
+//   1. key = the point's digits packed 3 bits each; one stable radix sort of (key, index); unique-by-key leaves the
+//      distinct leaves in path order, each with its smallest point index;
+//   2. a leaf whose key first differs from its predecessor's at digit t heads new nodes at depths t+1 .. levels: one
+//      scan numbers every node of the tree (temporary ids), a binary search finds the leaf heading the parent of the
+//      topmost new node;
+//   3. depth by depth from the leaves up, every node takes the minimum of its children's creators (at most eight
+//      contenders per address) and registers with its parent;
+//   4. temporary nodes are sorted by (creator, level) -- one radix sort -- which yields the reference's indices;
+//   5. children are renumbered and written straight into the traversal layout (octree_types.cuh: index +
+//      child-exists mask nibbles, model array).
+// No host round trip for the data: the paths may already live on the device.
 #pragma once
 #include "octree_types.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
 
 namespace qb
 {
 
 constexpr int BUILD_LEVELS = 12; // digits per point: oct14 / oct54 / oct94 (skeleton_vsh.c L212-226)
 
-__device__ __forceinline__ int path_digit(const int* __restrict__ p14, const int* __restrict__ p54,
-                                          const int* __restrict__ p94, size_t i, int level)
-{
-    // octree.c L153-156: levels 0-3 from the first buffer, 4-7 from the second, 8-11 from the third
-    const int* p = level < 4 ? p14 : (level < 8 ? p54 : p94);
-    return p[i * 4 + (level & 3)] & 7;
-}
-
-__global__ void build_propose_kernel(const int* __restrict__ p14, const int* __restrict__ p54,
-                                     const int* __restrict__ p94, size_t n, int level, const int* __restrict__ cur,
-                                     int level_base, int* __restrict__ table)
-{
-    size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
-    // slot this point proposes itself for; points beyond n propose nothing
-    long long slot = -1;
-    if (i < n) slot = (long long) (cur[i] - level_base) * 8 + path_digit(p14, p54, p94, i, level);
-    // Neighbouring points usually share the slot (the model is spatially sorted): within a warp indices
-    // ascend, so only the first lane of a run of equal slots can hold the minimum -- one atomic per run
-    // instead of one per point (the top levels would otherwise serialise 10 M atomics on 8 addresses).
-    const long long prev = __shfl_up_sync(0xffffffffu, slot, 1);
-    const bool      head = (threadIdx.x & 31) == 0 || prev != slot;
-    if (slot >= 0 && head) atomicMin(&table[slot], (int) i);
-}
-
-__global__ void build_flags_kernel(const int* __restrict__ table, size_t slots, int* __restrict__ flags)
-{
-    size_t j = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
-    if (j < slots) flags[j] = table[j] != 0x7fffffff;
-}
-
-__global__ void build_create_kernel(const int* __restrict__ table, const int* __restrict__ pos, size_t slots,
-                                    int level, int level_base, int next, int* __restrict__ tmp_child,
-                                    unsigned* __restrict__ tmp_key)
-{
-    size_t j = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
-    if (j >= slots) return;
-    const int creator = table[j];
-    if (creator == 0x7fffffff) return;
-    const int id                                             = next + pos[j];
-    tmp_child[(size_t) (level_base + (int) (j >> 3)) * 8 + (j & 7)] = id;
-    tmp_key[id] = ((unsigned) creator << 4) | (unsigned) level; // order of creation: (creator, level)
-}
-
-__global__ void build_step_kernel(const int* __restrict__ p14, const int* __restrict__ p54,
-                                  const int* __restrict__ p94, size_t n, int level, int* __restrict__ cur,
-                                  const int* __restrict__ tmp_child)
+// digits of one point packed most significant first (octree.c L153-156: levels 0-3 from the first buffer, 4-7 from
+// the second, 8-11 from the third); only `levels` digits take part
+__global__ void build_key_kernel(const int4* __restrict__ p14, const int4* __restrict__ p54,
+                                 const int4* __restrict__ p94, size_t n, int levels,
+                                 unsigned long long* __restrict__ keys, unsigned* __restrict__ vals)
 {
     size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
     if (i >= n) return;
-    cur[i] = tmp_child[(size_t) cur[i] * 8 + path_digit(p14, p54, p94, i, level)];
+    const int4 a = p14[i], b = p54[i], c = p94[i];
+    const int  d[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+    unsigned long long k = 0;
+#pragma unroll
+    for (int l = 0; l < 12; l++)
+        if (l < levels) k = (k << 3) | (unsigned long long) (d[l] & 7);
+    keys[i] = k;
+    vals[i] = (unsigned) i;
+}
+
+// K: distinct leaf keys in ascending order.  first_diff[k] = t: K[k] shares exactly t leading digits with K[k-1]
+// (0 for the first leaf), so leaf k heads new nodes at depths t+1 .. levels (depth = digits in the prefix).
+__global__ void build_leafinfo_kernel(const unsigned long long* __restrict__ K, int U, int levels,
+                                      unsigned char* __restrict__ first_diff, int* __restrict__ created)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= U) return;
+    int t = 0;
+    if (k > 0) t = levels - 1 - (63 - __clzll((long long) (K[k] ^ K[k - 1]))) / 3;
+    first_diff[k] = (unsigned char) t;
+    created[k]    = levels - t;
+}
+
+// The parent of leaf k's topmost new node (depth t+1) is the depth-t node holding k; it is headed by the first leaf
+// carrying k's t-digit prefix: a lower bound in the sorted keys.
+__global__ void build_parent_kernel(const unsigned long long* __restrict__ K, int U, int levels,
+                                    const unsigned char* __restrict__ first_diff, int* __restrict__ parent_leaf)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= U) return;
+    const int t = first_diff[k];
+    if (t == 0)
+    {
+        parent_leaf[k] = -1; // child of the root
+        return;
+    }
+    const int                sh     = 3 * (levels - t);
+    const unsigned long long prefix = (K[k] >> sh) << sh;
+    int                      lo = 0, hi = k; // K[k] >= prefix, the answer is in [0, k]
+    while (lo < hi)
+    {
+        const int mid = (lo + hi) >> 1;
+        if (K[mid] < prefix) lo = mid + 1;
+        else hi = mid;
+    }
+    parent_leaf[k] = lo;
+}
+
+// temporary id of the node at depth d headed by leaf k (exists iff first_diff[k] < d)
+__device__ __forceinline__ int build_tmp_id(const int* __restrict__ base, const unsigned char* __restrict__ first_diff,
+                                            int k, int d)
+{
+    return 1 + base[k] + (d - (int) first_diff[k] - 1);
+}
+
+// One depth, leaves upwards: creator[id] already holds the minimum over the node's other children (previous launch);
+// fold in the own chain, publish the creation key, register with the parent.
+__global__ void build_link_kernel(const unsigned long long* __restrict__ K, const unsigned* __restrict__ V, int U,
+                                  int levels, int d, const unsigned char* __restrict__ first_diff,
+                                  const int* __restrict__ base, const int* __restrict__ parent_leaf,
+                                  int* __restrict__ creator, int* __restrict__ tmp_child,
+                                  unsigned* __restrict__ tmp_key)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= U) return;
+    const int t = first_diff[k];
+    if (t >= d) return;
+    const int id = 1 + base[k] + (d - t - 1);
+    int       cr = d == levels ? (int) V[k] : creator[id + 1]; // the same leaf's node one depth down
+    cr           = min(cr, creator[id]);
+    creator[id]  = cr;
+    tmp_key[id]  = ((unsigned) cr << 4) | (unsigned) (d - 1); // order of creation: (creator, level)
+    const int digit = (int) ((K[k] >> (3 * (levels - d))) & 7ull);
+    int       parent;
+    if (d - 1 > t) parent = id - 1; // same chain; its creator is folded in by the next launch
+    else if (d == 1) parent = 0;
+    else
+    {
+        const int p = parent_leaf[k];
+        parent      = build_tmp_id(base, first_diff, p, d - 1);
+        atomicMin(&creator[parent], cr);
+    }
+    tmp_child[(size_t) parent * 8 + digit] = id;
 }
 
 __global__ void build_fill_kernel(int* __restrict__ v, size_t n, int value)

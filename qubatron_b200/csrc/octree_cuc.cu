@@ -1251,61 +1251,85 @@ size_t build_from_device_paths(Impl* I, int buftype, const int* p14, const int* 
 {
     const int    t  = tree_index(buftype);
     cudaStream_t st = I->stream;
-    // temporary tree: children by temporary id, creation key (creator << 4 | level) per node
-    size_t    cap       = n / 4 + 4096;
-    int*      tmp_child = scratch<int>(I, cap * 8);
-    unsigned* tmp_key   = scratch<unsigned>(I, cap);
-    CUDA_OK(cudaMemsetAsync(tmp_child, 0, cap * 8 * sizeof(int), st));
-    int* cur = scratch<int>(I, n);
-    CUDA_OK(cudaMemsetAsync(cur, 0, (n ? n : 1) * sizeof(int), st));
-
-    int    level_base = 0, level_count = 1, next = 1;
-    size_t launches = 0;
-    for (int level = 0; level < levels && n > 0; level++)
+    size_t       launches = 0;
+    int          total = 1; // nodes including the root
+    int*         tmp_child = nullptr; // children by temporary id
+    unsigned*    tmp_key   = nullptr; // creation key (creator << 4 | level) per temporary node
+    if (n > 0 && levels > 0)
     {
-        const size_t slots = (size_t) level_count * 8;
-        int*         table = scratch<int>(I, slots);
-        int*         flags = scratch<int>(I, slots);
-        int*         pos   = scratch<int>(I, slots);
-        build_fill_kernel<<<nblk(slots), 256, 0, st>>>(table, slots, 0x7fffffff);
-        build_propose_kernel<<<nblk(n), 256, 0, st>>>(p14, p54, p94, n, level, cur, level_base, table);
-        build_flags_kernel<<<nblk(slots), 256, 0, st>>>(table, slots, flags);
+        using u64 = unsigned long long;
+        // 1. (key, index) sorted by key, stable; distinct leaves with their smallest point index
+        u64*      keys_a = scratch<u64>(I, n);
+        u64*      keys_b = scratch<u64>(I, n);
+        unsigned* vals_a = scratch<unsigned>(I, n);
+        unsigned* vals_b = scratch<unsigned>(I, n);
+        build_key_kernel<<<nblk(n), 256, 0, st>>>((const int4*) p14, (const int4*) p54, (const int4*) p94, n, levels,
+                                                  keys_a, vals_a);
         size_t tb = 0;
-        CUDA_OK(cub::DeviceScan::ExclusiveSum(nullptr, tb, flags, pos, (int) slots, st));
+        CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, tb, keys_a, keys_b, vals_a, vals_b, (int) n, 0, 3 * levels, st));
         void* tmp = scratch<char>(I, tb);
-        CUDA_OK(cub::DeviceScan::ExclusiveSum(tmp, tb, flags, pos, (int) slots, st));
-        int last_pos = 0, last_flag = 0;
-        CUDA_OK(cudaMemcpyAsync(&last_pos, pos + slots - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
-        CUDA_OK(cudaMemcpyAsync(&last_flag, flags + slots - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
-        CUDA_OK(cudaStreamSynchronize(st));
-        const int created = last_pos + last_flag;
-        if ((size_t) next + created > cap)
-        {
-            size_t    ncap = ((size_t) next + created) * 2 + 4096;
-            int*      nc   = scratch<int>(I, ncap * 8);
-            unsigned* nk   = scratch<unsigned>(I, ncap);
-            CUDA_OK(cudaMemsetAsync(nc, 0, ncap * 8 * sizeof(int), st));
-            CUDA_OK(cudaMemcpyAsync(nc, tmp_child, (size_t) next * 8 * sizeof(int), cudaMemcpyDeviceToDevice, st));
-            CUDA_OK(cudaMemcpyAsync(nk, tmp_key, (size_t) next * sizeof(unsigned), cudaMemcpyDeviceToDevice, st));
-            scratch_free(I, tmp_child);
-            scratch_free(I, tmp_key);
-            tmp_child = nc, tmp_key = nk, cap = ncap;
-        }
-        build_create_kernel<<<nblk(slots), 256, 0, st>>>(table, pos, slots, level, level_base, next, tmp_child, tmp_key);
-        build_step_kernel<<<nblk(n), 256, 0, st>>>(p14, p54, p94, n, level, cur, tmp_child);
-        CUDA_OK(cudaGetLastError());
-        launches += 6;
+        CUDA_OK(cub::DeviceRadixSort::SortPairs(tmp, tb, keys_a, keys_b, vals_a, vals_b, (int) n, 0, 3 * levels, st));
         scratch_free(I, tmp);
-        scratch_free(I, table);
-        scratch_free(I, flags);
-        scratch_free(I, pos);
-        level_base  = next;
-        level_count = created;
-        next += created;
-        if (created == 0) break;
+        int* counts = scratch<int>(I, 4);
+        tb          = 0;
+        CUDA_OK(cub::DeviceSelect::UniqueByKey(nullptr, tb, keys_b, vals_b, keys_a, vals_a, counts, (int) n, st));
+        tmp = scratch<char>(I, tb);
+        CUDA_OK(cub::DeviceSelect::UniqueByKey(tmp, tb, keys_b, vals_b, keys_a, vals_a, counts, (int) n, st));
+        scratch_free(I, tmp);
+        int U = 0;
+        CUDA_OK(cudaMemcpyAsync(&U, counts, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaStreamSynchronize(st));
+        const u64*      K = keys_a;
+        const unsigned* V = vals_a;
+
+        // 2. nodes every leaf heads, temporary ids by one scan, parent links
+        unsigned char* first_diff  = scratch<unsigned char>(I, (size_t) U);
+        int*           created     = scratch<int>(I, (size_t) U);
+        int*           base        = scratch<int>(I, (size_t) U);
+        int*           parent_leaf = scratch<int>(I, (size_t) U);
+        build_leafinfo_kernel<<<nblk(U), 256, 0, st>>>(K, U, levels, first_diff, created);
+        tb = 0;
+        CUDA_OK(cub::DeviceScan::ExclusiveSum(nullptr, tb, created, base, U, st));
+        tmp = scratch<char>(I, tb);
+        CUDA_OK(cub::DeviceScan::ExclusiveSum(tmp, tb, created, base, U, st));
+        scratch_free(I, tmp);
+        build_parent_kernel<<<nblk(U), 256, 0, st>>>(K, U, levels, first_diff, parent_leaf);
+        int last[2] = {0, 0};
+        CUDA_OK(cudaMemcpyAsync(&last[0], base + (U - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaMemcpyAsync(&last[1], created + (U - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaStreamSynchronize(st));
+        total = 1 + last[0] + last[1];
+
+        // 3. creators and child tables, leaves upwards
+        tmp_child    = scratch<int>(I, (size_t) total * 8);
+        tmp_key      = scratch<unsigned>(I, (size_t) total);
+        int* creator = scratch<int>(I, (size_t) total);
+        CUDA_OK(cudaMemsetAsync(tmp_child, 0, (size_t) total * 8 * sizeof(int), st));
+        build_fill_kernel<<<nblk(total), 256, 0, st>>>(creator, (size_t) total, 0x7fffffff);
+        for (int d = levels; d >= 1; d--)
+            build_link_kernel<<<nblk(U), 256, 0, st>>>(K, V, U, levels, d, first_diff, base, parent_leaf, creator,
+                                                       tmp_child, tmp_key);
+        CUDA_OK(cudaGetLastError());
+        launches += 8 + (size_t) levels;
+        scratch_free(I, creator);
+        scratch_free(I, parent_leaf);
+        scratch_free(I, base);
+        scratch_free(I, created);
+        scratch_free(I, first_diff);
+        scratch_free(I, counts);
+        scratch_free(I, vals_b);
+        scratch_free(I, vals_a);
+        scratch_free(I, keys_b);
+        scratch_free(I, keys_a);
+    }
+    else
+    {
+        tmp_child = scratch<int>(I, 8);
+        tmp_key   = scratch<unsigned>(I, 1);
+        CUDA_OK(cudaMemsetAsync(tmp_child, 0, 8 * sizeof(int), st));
     }
 
-    const int total = next; // nodes including the root
+
     // reference numbering = rank in (creator, level) order
     int* final_of_tmp = scratch<int>(I, (size_t) total);
     if (total > 1)
@@ -1340,7 +1364,6 @@ size_t build_from_device_paths(Impl* I, int buftype, const int* p14, const int* 
     I->launches += launches;
 
     scratch_free(I, final_of_tmp);
-    scratch_free(I, cur);
     scratch_free(I, tmp_child);
     scratch_free(I, tmp_key);
     return (size_t) total;
