@@ -36,10 +36,13 @@ namespace qb
 constexpr int BUILD_LEVELS = 12; // digits per point: oct14 / oct54 / oct94 (skeleton_vsh.c L212-226)
 
 // digits of one point packed most significant first (octree.c L153-156: levels 0-3 from the first buffer, 4-7 from
-// the second, 8-11 from the third); only `levels` digits take part
+// the second, 8-11 from the third) above the point's index: one 64-bit word per point, so the sort moves keys only
+// and, being stable on the path bits, leaves equal paths in index order.  36 path bits + 28 index bits.
+constexpr int BUILD_INDEX_BITS = 28;
+
 __global__ void build_key_kernel(const int4* __restrict__ p14, const int4* __restrict__ p54,
                                  const int4* __restrict__ p94, size_t n, int levels,
-                                 unsigned long long* __restrict__ keys, unsigned* __restrict__ vals)
+                                 unsigned long long* __restrict__ keys)
 {
     size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -49,11 +52,19 @@ __global__ void build_key_kernel(const int4* __restrict__ p14, const int4* __res
 #pragma unroll
     for (int l = 0; l < 12; l++)
         if (l < levels) k = (k << 3) | (unsigned long long) (d[l] & 7);
-    keys[i] = k;
-    vals[i] = (unsigned) i;
+    keys[i] = (k << BUILD_INDEX_BITS) | (unsigned long long) i;
 }
 
-// K: distinct leaf keys in ascending order.  first_diff[k] = t: K[k] shares exactly t leading digits with K[k-1]
+// sorted (path, index) words -> 1 for the first word of every distinct path
+__global__ void build_head_flags_kernel(const unsigned long long* __restrict__ sorted, size_t n,
+                                        unsigned char* __restrict__ flags)
+{
+    size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    flags[i] = i == 0 || (sorted[i] >> BUILD_INDEX_BITS) != (sorted[i - 1] >> BUILD_INDEX_BITS);
+}
+
+// K: the distinct leaves in ascending path order, each word = path << 28 | smallest point index.  first_diff[k] = t: K[k] shares exactly t leading digits with K[k-1]
 // (0 for the first leaf), so leaf k heads new nodes at depths t+1 .. levels (depth = digits in the prefix).
 __global__ void build_leafinfo_kernel(const unsigned long long* __restrict__ K, int U, int levels,
                                       unsigned char* __restrict__ first_diff, int* __restrict__ created)
@@ -61,7 +72,8 @@ __global__ void build_leafinfo_kernel(const unsigned long long* __restrict__ K, 
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= U) return;
     int t = 0;
-    if (k > 0) t = levels - 1 - (63 - __clzll((long long) (K[k] ^ K[k - 1]))) / 3;
+    if (k > 0)
+        t = levels - 1 - (63 - __clzll((long long) ((K[k] >> BUILD_INDEX_BITS) ^ (K[k - 1] >> BUILD_INDEX_BITS)))) / 3;
     first_diff[k] = (unsigned char) t;
     created[k]    = levels - t;
 }
@@ -79,8 +91,8 @@ __global__ void build_parent_kernel(const unsigned long long* __restrict__ K, in
         parent_leaf[k] = -1; // child of the root
         return;
     }
-    const int                sh     = 3 * (levels - t);
-    const unsigned long long prefix = (K[k] >> sh) << sh;
+    const int                sh     = 3 * (levels - t) + BUILD_INDEX_BITS;
+    const unsigned long long prefix = (K[k] >> sh) << sh; // index bits zero: below every word with this prefix
     int                      lo = 0, hi = k; // K[k] >= prefix, the answer is in [0, k]
     while (lo < hi)
     {
@@ -100,8 +112,7 @@ __device__ __forceinline__ int build_tmp_id(const int* __restrict__ base, const 
 
 // One depth, leaves upwards: creator[id] already holds the minimum over the node's other children (previous launch);
 // fold in the own chain, publish the creation key, register with the parent.
-__global__ void build_link_kernel(const unsigned long long* __restrict__ K, const unsigned* __restrict__ V, int U,
-                                  int levels, int d, const unsigned char* __restrict__ first_diff,
+__global__ void build_link_kernel(const unsigned long long* __restrict__ K, int U, int levels, int d, const unsigned char* __restrict__ first_diff,
                                   const int* __restrict__ base, const int* __restrict__ parent_leaf,
                                   int* __restrict__ creator, int* __restrict__ tmp_child,
                                   unsigned* __restrict__ tmp_key)
@@ -111,11 +122,12 @@ __global__ void build_link_kernel(const unsigned long long* __restrict__ K, cons
     const int t = first_diff[k];
     if (t >= d) return;
     const int id = 1 + base[k] + (d - t - 1);
-    int       cr = d == levels ? (int) V[k] : creator[id + 1]; // the same leaf's node one depth down
+    const unsigned long long w = K[k];
+    int cr = d == levels ? (int) (w & ((1ull << BUILD_INDEX_BITS) - 1)) : creator[id + 1]; // own node one depth down
     cr           = min(cr, creator[id]);
     creator[id]  = cr;
     tmp_key[id]  = ((unsigned) cr << 4) | (unsigned) (d - 1); // order of creation: (creator, level)
-    const int digit = (int) ((K[k] >> (3 * (levels - d))) & 7ull);
+    const int digit = (int) ((w >> (3 * (levels - d) + BUILD_INDEX_BITS)) & 7ull);
     int       parent;
     if (d - 1 > t) parent = id - 1; // same chain; its creator is folded in by the next launch
     else if (d == 1) parent = 0;

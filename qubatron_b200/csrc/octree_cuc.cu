@@ -1258,29 +1258,32 @@ size_t build_from_device_paths(Impl* I, int buftype, const int* p14, const int* 
     if (n > 0 && levels > 0)
     {
         using u64 = unsigned long long;
-        // 1. (key, index) sorted by key, stable; distinct leaves with their smallest point index
-        u64*      keys_a = scratch<u64>(I, n);
-        u64*      keys_b = scratch<u64>(I, n);
-        unsigned* vals_a = scratch<unsigned>(I, n);
-        unsigned* vals_b = scratch<unsigned>(I, n);
+        // 1. one word per point (path << 28 | index) sorted on the path bits; the first word of every distinct path
+        //    carries the smallest index
+        u64* keys_a = scratch<u64>(I, n);
+        u64* keys_b = scratch<u64>(I, n);
         build_key_kernel<<<nblk(n), 256, 0, st>>>((const int4*) p14, (const int4*) p54, (const int4*) p94, n, levels,
-                                                  keys_a, vals_a);
+                                                  keys_a);
         size_t tb = 0;
-        CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, tb, keys_a, keys_b, vals_a, vals_b, (int) n, 0, 3 * levels, st));
+        CUDA_OK(cub::DeviceRadixSort::SortKeys(nullptr, tb, keys_a, keys_b, (int) n, BUILD_INDEX_BITS,
+                                               BUILD_INDEX_BITS + 3 * levels, st));
         void* tmp = scratch<char>(I, tb);
-        CUDA_OK(cub::DeviceRadixSort::SortPairs(tmp, tb, keys_a, keys_b, vals_a, vals_b, (int) n, 0, 3 * levels, st));
+        CUDA_OK(cub::DeviceRadixSort::SortKeys(tmp, tb, keys_a, keys_b, (int) n, BUILD_INDEX_BITS,
+                                               BUILD_INDEX_BITS + 3 * levels, st));
         scratch_free(I, tmp);
+        unsigned char* heads = scratch<unsigned char>(I, n);
+        build_head_flags_kernel<<<nblk(n), 256, 0, st>>>(keys_b, n, heads);
         int* counts = scratch<int>(I, 4);
         tb          = 0;
-        CUDA_OK(cub::DeviceSelect::UniqueByKey(nullptr, tb, keys_b, vals_b, keys_a, vals_a, counts, (int) n, st));
+        CUDA_OK(cub::DeviceSelect::Flagged(nullptr, tb, keys_b, heads, keys_a, counts, (int) n, st));
         tmp = scratch<char>(I, tb);
-        CUDA_OK(cub::DeviceSelect::UniqueByKey(tmp, tb, keys_b, vals_b, keys_a, vals_a, counts, (int) n, st));
+        CUDA_OK(cub::DeviceSelect::Flagged(tmp, tb, keys_b, heads, keys_a, counts, (int) n, st));
         scratch_free(I, tmp);
+        scratch_free(I, heads);
         int U = 0;
         CUDA_OK(cudaMemcpyAsync(&U, counts, sizeof(int), cudaMemcpyDeviceToHost, st));
         CUDA_OK(cudaStreamSynchronize(st));
-        const u64*      K = keys_a;
-        const unsigned* V = vals_a;
+        const u64* K = keys_a;
 
         // 2. nodes every leaf heads, temporary ids by one scan, parent links
         unsigned char* first_diff  = scratch<unsigned char>(I, (size_t) U);
@@ -1307,18 +1310,16 @@ size_t build_from_device_paths(Impl* I, int buftype, const int* p14, const int* 
         CUDA_OK(cudaMemsetAsync(tmp_child, 0, (size_t) total * 8 * sizeof(int), st));
         build_fill_kernel<<<nblk(total), 256, 0, st>>>(creator, (size_t) total, 0x7fffffff);
         for (int d = levels; d >= 1; d--)
-            build_link_kernel<<<nblk(U), 256, 0, st>>>(K, V, U, levels, d, first_diff, base, parent_leaf, creator,
+            build_link_kernel<<<nblk(U), 256, 0, st>>>(K, U, levels, d, first_diff, base, parent_leaf, creator,
                                                        tmp_child, tmp_key);
         CUDA_OK(cudaGetLastError());
-        launches += 8 + (size_t) levels;
+        launches += 9 + (size_t) levels;
         scratch_free(I, creator);
         scratch_free(I, parent_leaf);
         scratch_free(I, base);
         scratch_free(I, created);
         scratch_free(I, first_diff);
         scratch_free(I, counts);
-        scratch_free(I, vals_b);
-        scratch_free(I, vals_a);
         scratch_free(I, keys_b);
         scratch_free(I, keys_a);
     }
@@ -1549,6 +1550,10 @@ void bone_consts(const float* ob, const float* nb, int div, BoneConsts* out10)
         c.oldbone[0] = oldbone.x, c.oldbone[1] = oldbone.y, c.oldbone[2] = oldbone.z;
         c.midp[0] = midp.x, c.midp[1] = midp.y, c.midp[2] = midp.z;
         c.half_len = hdiv(hlen(oldbone), 2.0f, div);
+        {
+            const double r = (double) c.half_len + fabs((double) ob[i * 4 + 3]) + 1.0;
+            c.cull_r2      = (float) (r * r * 1.001);
+        }
         c.ab_dot   = hdot(oldbone, oldbone);
         c.newa[0] = na.x, c.newa[1] = na.y, c.newa[2] = na.z;
         hquat(on, nb[i * 4 + 3], c.rot_quat);

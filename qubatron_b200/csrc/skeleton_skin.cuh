@@ -25,6 +25,7 @@ struct BoneConsts
     float rot_quat[4];  // rotation about the old bone by newbones[i].w
     int   has_axis;     // bones not parallel
     float axis_quat[4]; // rotation old bone -> current bone
+    float cull_r2;      // (half_len + effect + 1)^2, rounded up: farther from midp than this cannot be in range
 };
 
 struct SkinParams
@@ -68,7 +69,14 @@ __global__ void skin_kernel(const SkinParams S, size_t n, const float* __restric
 #pragma unroll 1
     for (int k = 0; k < 10; k++)
     {
-        const BoneConsts& c  = S.bones[k];
+        const BoneConsts& c = S.bones[k];
+        // Exact cull.  In real arithmetic `dist` below is the distance to the bone SEGMENT (perpendicular distance
+        // when the foot lies inside it, else the nearer end), hence >= |position - midp| - half_len.  A point
+        // farther from midp than half_len + effect + 1 has dist > effect + 1; fp32 rounding of dist is orders of
+        // magnitude below that margin, so the reference takes the `diff >= 0` branch and the bone contributes
+        // nothing.  (NaN compares false and falls through to the full evaluation.)
+        const float3 from_mid = sub3(position, ld3(c.midp));
+        if (dot3(from_mid, from_mid) > c.cull_r2) continue;
         const float3      A  = ld3(c.a);
         const float3      AB = ld3(c.oldbone);
         const float3      AC = sub3(position, A);
