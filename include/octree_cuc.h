@@ -261,6 +261,27 @@ size_t octree_cuc_skeleton_update(octree_glc_t* rc, const float* oldbones80, con
 size_t octree_cuc_skeleton_read_out(octree_glc_t* rc, int32_t* oct14, int32_t* oct54, int32_t* oct94, float* nrm_out,
                                     float* pnt_out);
 
+/* "Next" row: the particle and dust simulation steps of the reference's transform-feedback programs
+ * (shaders/particle_vsh.c dispatched by particle_glc.c L118-156 over the octree texture that octree_glc.c bound,
+ * L105-113; shaders/dust_vsh.c dispatched by dust_glc.c L103-135).  `kind` selects the program.
+ *   octree_cuc_particles_alloc_in   replaces particle_glc_alloc_in / dust_glc_alloc_in: positions and speeds,
+ *                                   float[3] each, `bytes` = size of ONE of the two arrays
+ *   octree_cuc_particles_update     replaces particle_glc_update / dust_glc_update: `steps` simulation steps over the
+ *                                   first `count` particles, state kept on the device (the reference round-trips it
+ *                                   through the host every frame, modelutil.c L715-724); campos is used by dust only
+ *   octree_cuc_particles_read_out   the programs' two output buffers (either may be NULL); for OCTREE_CUC_PARTICLES
+ *                                   returns how many of the `count` particles the last step left parked
+ *                                   (speed.x < -900, the host's end-of-simulation test, modelutil.c L730-744) */
+enum
+{
+    OCTREE_CUC_PARTICLES = 0, /* particle_vsh.c */
+    OCTREE_CUC_DUST      = 1  /* dust_vsh.c */
+};
+void   octree_cuc_particles_alloc_in(octree_glc_t* rc, int kind, const float* posdata, const float* spddata, size_t bytes);
+void   octree_cuc_particles_update(octree_glc_t* rc, int kind, int count, int maxlevel, float basesize, v3_t campos,
+                                   int steps);
+size_t octree_cuc_particles_read_out(octree_glc_t* rc, int kind, int count, float* pos_out, float* spd_out);
+
 /* "Next" row: the offline voxeliser qmc (qmc.c: grid index at 2 * 2^levels cells per axis,
  * drop points outside the cube, x-major sort, first point of every occupied cell, colour = uchar / 255.0) and
  * the bulk tree build (octree_insert_point order) on the GPU, straight into the renderer's arrays.  pos / nrm:

@@ -24,7 +24,8 @@
  *   mode 3 : aux dump of the shadow visibility step(sqr, 15.0)
  *   The aux modes append statements that copy a value to the output; the traversal
  *   and shading code is untouched.
- *   mode 20 / 21 : skeleton_vsh.c through transform feedback (see skin_main below)
+ *   mode 20 - 22 : skeleton_vsh.c through transform feedback (see skin_main below)
+ *   mode 30 / 31 : particle_vsh.c / dust_vsh.c through transform feedback (see particle_main below)
  * prints one JSON line with renderer, version and per-frame seconds.
  */
 #define _GNU_SOURCE
@@ -40,6 +41,10 @@ extern const char _binary_octree_fsh_c_start[], _binary_octree_fsh_c_end[];
 extern const char _binary_octree_vsh_c_start[], _binary_octree_vsh_c_end[];
 extern const char _binary_skeleton_vsh_c_start[], _binary_skeleton_vsh_c_end[];
 extern const char _binary_skeleton_fsh_c_start[], _binary_skeleton_fsh_c_end[];
+extern const char _binary_particle_vsh_c_start[], _binary_particle_vsh_c_end[];
+extern const char _binary_particle_fsh_c_start[], _binary_particle_fsh_c_end[];
+extern const char _binary_dust_vsh_c_start[], _binary_dust_vsh_c_end[];
+extern const char _binary_dust_fsh_c_start[], _binary_dust_fsh_c_end[];
 
 #ifndef MESA_DIR
     #define MESA_DIR "/opt/nvidia/nsight-compute/2025.2.1/host/linux-desktop-glibc_2_11_3-x64/Mesa"
@@ -411,12 +416,122 @@ static int skin_main(const char* in, const char* outp, int mode, int repeat)
     return 0;
 }
 
+/*
+ * mode 30 / 31: the reference's particle (particle_vsh.c) and dust (dust_vsh.c) simulation steps through transform
+ * feedback, restating the host side of /root/reference/src/qubatron/particle_glc.c L43-113 (program, the two
+ * varyings, VAO, static octree sampler on unit 11 = octree_glc.c's texture), L118-156 (uniforms, GL_POINTS draw with
+ * rasterizer discard, read-back) and dust_glc.c L103-135.
+ *   in.bin : int64 hdr[3] = {n, maxlevel, nodes_s}; float f[4] = {basesize, campos.xyz};
+ *            float pos[3n], spd[3n]; int32 oct_s[12 * nodes_s]
+ *   out    : float pos_out[3n], spd_out[3n]
+ */
+static int particle_main(const char* in, const char* outp, int mode, int repeat)
+{
+    FILE* f = fopen(in, "rb");
+    if (!f) die("cannot open input");
+    int64_t hdr[3];
+    float   fb[4];
+    if (fread(hdr, 8, 3, f) != 3 || fread(fb, 4, 4, f) != 4) die("short particle input header");
+    size_t   n = (size_t) hdr[0], nodes = (size_t) hdr[2];
+    float*   pos = malloc((n ? n : 1) * 12);
+    float*   spd = malloc((n ? n : 1) * 12);
+    int32_t* oct = malloc((nodes ? nodes : 1) * 48);
+    if (fread(pos, 12, n, f) != n || fread(spd, 12, n, f) != n || fread(oct, 48, nodes, f) != nodes)
+        die("short particle input body");
+    fclose(f);
+
+    gl_context();
+    char* vsh = mode == 30 ? embedded(_binary_particle_vsh_c_start, _binary_particle_vsh_c_end)
+                           : embedded(_binary_dust_vsh_c_start, _binary_dust_vsh_c_end);
+    char* fsh = mode == 30 ? embedded(_binary_particle_fsh_c_start, _binary_particle_fsh_c_end)
+                           : embedded(_binary_dust_fsh_c_start, _binary_dust_fsh_c_end);
+    GLuint prog = glCreateProgram();
+    glAttachShader(prog, compile(GL_VERTEX_SHADER, vsh));
+    glAttachShader(prog, compile(GL_FRAGMENT_SHADER, fsh));
+    const GLchar* vary[2] = {"pos_out", "spd_out"};
+    glTransformFeedbackVaryings(prog, 2, vary, GL_SEPARATE_ATTRIBS);
+    glBindAttribLocation(prog, 0, "pos");
+    glBindAttribLocation(prog, 1, "spd");
+    glLinkProgram(prog);
+    GLint ok = 0;
+    glGetProgramiv(prog, GL_LINK_STATUS, &ok);
+    if (!ok)
+    {
+        char log[4096];
+        glGetProgramInfoLog(prog, sizeof(log), NULL, log);
+        fprintf(stderr, "glsl_ref: link failed:\n%s\n", log);
+        return 2;
+    }
+    glUseProgram(prog);
+    glPixelStorei(GL_UNPACK_ALIGNMENT, 1);
+    if (mode == 30)
+    {
+        data_texture(11, oct, nodes * 3, 1);
+        glUniform1i(glGetUniformLocation(prog, "octtexbuf_s"), 11); /* particle_glc.c L106-107 */
+        glUniform1i(glGetUniformLocation(prog, "octtexbuf_d"), 12);
+    }
+
+    GLuint vin[2], vao, vout[2];
+    glGenBuffers(2, vin);
+    glGenVertexArrays(1, &vao);
+    glBindVertexArray(vao);
+    glBindBuffer(GL_ARRAY_BUFFER, vin[0]);
+    glBufferData(GL_ARRAY_BUFFER, (GLsizeiptr) (n * 12), pos, GL_STATIC_DRAW);
+    glEnableVertexAttribArray(0);
+    glVertexAttribPointer(0, 3, GL_FLOAT, 0, sizeof(GLfloat) * 3, 0);
+    glBindBuffer(GL_ARRAY_BUFFER, vin[1]);
+    glBufferData(GL_ARRAY_BUFFER, (GLsizeiptr) (n * 12), spd, GL_STATIC_DRAW);
+    glEnableVertexAttribArray(1);
+    glVertexAttribPointer(1, 3, GL_FLOAT, 0, sizeof(GLfloat) * 3, 0);
+    glGenBuffers(2, vout);
+    for (int i = 0; i < 2; i++)
+    {
+        glBindBuffer(GL_ARRAY_BUFFER, vout[i]);
+        glBufferData(GL_ARRAY_BUFFER, (GLsizeiptr) (n ? n * 12 : 16), NULL, GL_STREAM_READ);
+    }
+    glBindBuffer(GL_ARRAY_BUFFER, 0);
+
+    glEnable(GL_RASTERIZER_DISCARD);
+    GLfloat basecube[4] = {0.0f, fb[0], fb[0], fb[0]};
+    glUniform4fv(glGetUniformLocation(prog, "basecube"), 1, basecube);
+    glUniform1i(glGetUniformLocation(prog, "maxlevel"), (GLint) hdr[1]);
+    if (mode == 31) glUniform3fv(glGetUniformLocation(prog, "campos"), 1, fb + 1);
+    for (int i = 0; i < 2; i++) glBindBufferBase(GL_TRANSFORM_FEEDBACK_BUFFER, (GLuint) i, vout[i]);
+
+    printf("{\"renderer\": \"%s\", \"version\": \"%s\", \"mode\": %d, \"frame_s\": [", glGetString(GL_RENDERER),
+           glGetString(GL_VERSION), mode);
+    for (int r = 0; r < repeat; r++)
+    {
+        double t0 = now();
+        glBeginTransformFeedback(GL_POINTS);
+        glDrawArrays(GL_POINTS, 0, (GLsizei) n);
+        glEndTransformFeedback();
+        glFinish();
+        printf("%s%.6f", r ? ", " : "", now() - t0);
+    }
+    printf("], \"gl_error\": %u}\n", glGetError());
+
+    f = fopen(outp, "wb");
+    if (!f) die("cannot open output");
+    for (int i = 0; i < 2; i++)
+    {
+        void* host = malloc(n ? n * 12 : 16);
+        glBindBuffer(GL_TRANSFORM_FEEDBACK_BUFFER, vout[i]);
+        glGetBufferSubData(GL_TRANSFORM_FEEDBACK_BUFFER, 0, (GLsizeiptr) (n * 12), host);
+        fwrite(host, 1, n * 12, f);
+        free(host);
+    }
+    fclose(f);
+    return 0;
+}
+
 int main(int argc, char** argv)
 {
     if (argc < 3) die("usage: glsl_ref in.bin out.rgba [mode] [repeat]");
     int mode   = argc > 3 ? atoi(argv[3]) : 0;
     int repeat = argc > 4 ? atoi(argv[4]) : 1;
     if (mode >= 20 && mode <= 22) return skin_main(argv[1], argv[2], mode, repeat);
+    if (mode == 30 || mode == 31) return particle_main(argv[1], argv[2], mode, repeat);
 
     /* ---- input ---- */
     FILE* f = fopen(argv[1], "rb");

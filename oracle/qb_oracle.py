@@ -76,6 +76,9 @@ def lib(div=DIV_GLSL):
         l.qb_oracle_skin_rot.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         l.qb_oracle_bone_rotations.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        l.qb_oracle_particles.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int64, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        l.qb_oracle_dust.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _libs[div] = l
     return _libs[div]
 
@@ -165,6 +168,31 @@ def skin(oldbones, newbones, positions, normals, maxlevel=12, basesize=1800.0, d
     lib(div).qb_oracle_skin_rot(_ptr(ob), _ptr(nb), None if rot is None else _ptr(rot), _ptr(cube), int(maxlevel), n,
                                 _ptr(pos), _ptr(nrm), _ptr(digits), _ptr(nout), _ptr(pout))
     return digits, nout, pout
+
+
+def particles(oct_s, pos, spd, maxlevel=12, basesize=1800.0, div=DIV_GLSL):
+    """particle_vsh.c main() for n particles over the static tree `oct_s` (int32 [nodes,12]):
+    (pos_out f32[n,3], spd_out f32[n,3], stuck int32[n])."""
+    oct_s = np.ascontiguousarray(oct_s, dtype=np.int32).reshape(-1, 12)
+    pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 3)
+    spd = np.ascontiguousarray(spd, dtype=np.float32).reshape(-1, 3)
+    n = len(pos)
+    cube = np.array([0.0, basesize, basesize, basesize], dtype=np.float32)
+    po, so, hit = np.zeros((n, 3), np.float32), np.zeros((n, 3), np.float32), np.zeros(n, np.int32)
+    lib(div).qb_oracle_particles(_ptr(oct_s), len(oct_s), _ptr(cube), int(maxlevel), n, _ptr(pos), _ptr(spd), _ptr(po),
+                                 _ptr(so), _ptr(hit))
+    return po, so, hit
+
+
+def dust(campos, pos, spd, div=DIV_GLSL):
+    """dust_vsh.c main(): (pos_out, spd_out)."""
+    pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 3)
+    spd = np.ascontiguousarray(spd, dtype=np.float32).reshape(-1, 3)
+    cam = np.array(list(campos), dtype=np.float32)
+    n = len(pos)
+    po, so = np.zeros((n, 3), np.float32), np.zeros((n, 3), np.float32)
+    lib(div).qb_oracle_dust(_ptr(cam), n, _ptr(pos), _ptr(spd), _ptr(po), _ptr(so))
+    return po, so
 
 
 def pixel_rays(u):
@@ -380,3 +408,34 @@ def glsl_bone_rotations(oldbones, newbones, positions, normals, workdir=None):
             out[k, 4:8] = aq[j]
             out[k, 8] = float(ident[j, 1])
     return out, seen
+
+
+def glsl_particles(oct_s, pos, spd, maxlevel=12, basesize=1800.0, dust_campos=None, repeat=1, workdir=None):
+    """Run the reference's particle step (particle_vsh.c) -- or, with dust_campos, its dust step (dust_vsh.c) --
+    unmodified through transform feedback on llvmpipe (glsl_ref modes 30 / 31). Returns (pos_out, spd_out, info)."""
+    import json
+    import tempfile
+    oct_s = np.ascontiguousarray(oct_s, dtype=np.int32).reshape(-1, 12)
+    pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 3)
+    spd = np.ascontiguousarray(spd, dtype=np.float32).reshape(-1, 3)
+    n = len(pos)
+    mode = 30 if dust_campos is None else 31
+    cam = [0.0, 0.0, 0.0] if dust_campos is None else list(dust_campos)
+    with tempfile.TemporaryDirectory(dir=workdir) as d:
+        fin, fout = os.path.join(d, "in.bin"), os.path.join(d, "out.bin")
+        with open(fin, "wb") as f:
+            f.write(np.array([n, maxlevel, len(oct_s) if mode == 30 else 0], dtype=np.int64).tobytes())
+            f.write(np.array([basesize] + cam, dtype=np.float32).tobytes())
+            f.write(pos.tobytes())
+            f.write(spd.tobytes())
+            if mode == 30:
+                f.write(oct_s.tobytes())
+        r = subprocess.run([REF_GLSL, fin, fout, str(mode), str(repeat)], stdout=subprocess.PIPE,
+                           stderr=subprocess.PIPE, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("glsl_ref failed (%d): %s" % (r.returncode, r.stderr[-2000:]))
+        info = json.loads(r.stdout.strip().splitlines()[-1])
+        if info["gl_error"]:
+            raise RuntimeError("glsl_ref: GL error %d" % info["gl_error"])
+        raw = np.fromfile(fout, dtype=np.float32)
+    return raw[:3 * n].reshape(n, 3).copy(), raw[3 * n:].reshape(n, 3).copy(), info

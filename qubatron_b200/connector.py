@@ -29,6 +29,7 @@ AUX_STRIDE = 6
 
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FAST = 0, 1, 2
 DIV_GLSL, DIV_IEEE = 0, 1
+PARTICLES, DUST = 0, 1          # octree_cuc_particles_*: particle_vsh.c / dust_vsh.c
 
 
 class v3_t(C.Structure):
@@ -89,6 +90,10 @@ _PROTOS = {
                                                 C.c_float, C.c_int]),
     "octree_cuc_skeleton_read_out": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_void_p, C.c_void_p, C.c_void_p,
                                                   C.c_void_p, C.c_void_p]),
+    "octree_cuc_particles_alloc_in": (None, [C.POINTER(octree_glc_t), C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "octree_cuc_particles_update": (None, [C.POINTER(octree_glc_t), C.c_int, C.c_int, C.c_int, C.c_float, v3_t,
+                                           C.c_int]),
+    "octree_cuc_particles_read_out": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "octree_cuc_voxelise_and_build": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_void_p, C.c_void_p, C.c_void_p,
                                                    C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                                    C.c_void_p]),
@@ -342,6 +347,30 @@ class OctreeGlc:
                                               p94.ctypes.data_as(C.c_void_p), nrm.ctypes.data_as(C.c_void_p),
                                               pnt.ctypes.data_as(C.c_void_p))
         return np.concatenate([p14, p54, p94], axis=1), nrm, pnt
+
+    def particles_alloc_in(self, pos, spd, kind=PARTICLES):
+        pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 3)
+        spd = np.ascontiguousarray(spd, dtype=np.float32).reshape(-1, 3)
+        assert pos.shape == spd.shape
+        self.lib.octree_cuc_particles_alloc_in(self._p, int(kind), pos.ctypes.data_as(C.c_void_p),
+                                               spd.ctypes.data_as(C.c_void_p), pos.nbytes)
+        self._part_n = getattr(self, "_part_n", {})
+        self._part_n[int(kind)] = len(pos)
+
+    def particles_update(self, kind=PARTICLES, count=None, maxlevel=12, basesize=1800.0, campos=(0.0, 0.0, 0.0),
+                         steps=1):
+        n = self._part_n[int(kind)] if count is None else int(count)
+        self.lib.octree_cuc_particles_update(self._p, int(kind), n, int(maxlevel), float(basesize), v3_t(*campos),
+                                             int(steps))
+
+    def particles_read_out(self, kind=PARTICLES, count=None):
+        """(pos_out f32 [n,3], spd_out f32 [n,3], parked) -- parked only for PARTICLES."""
+        n = self._part_n[int(kind)] if count is None else int(count)
+        pos = np.zeros((n, 3), np.float32)
+        spd = np.zeros((n, 3), np.float32)
+        fin = self.lib.octree_cuc_particles_read_out(self._p, int(kind), n, pos.ctypes.data_as(C.c_void_p),
+                                                     spd.ctypes.data_as(C.c_void_p))
+        return pos, spd, int(fin)
 
     def voxelise_and_build(self, pos, col_u8, nrm, size=1800, levels=12, dynamic=False, want_order=True):
         """qmc + bulk tree build on the GPU from raw host arrays; returns (count, order int64[m], pos f32[m,3])."""

@@ -11,6 +11,7 @@
 #include "octree_render.cuh"
 #include "octree_trace_fast.cuh"
 #include "skeleton_skin.cuh"
+#include "particle_sim.cuh"
 
 #include <chrono>
 #include <cmath>
@@ -270,6 +271,12 @@ struct Impl
     int4 * skin_p14 = nullptr, *skin_p54 = nullptr, *skin_p94 = nullptr;
     float* skin_pnt_out = nullptr;
     size_t skin_count   = 0; // points of the last update
+    // particle / dust simulation state ("next" row 8f #2): [kind][in, out] position and speed, ping-pong
+    float*    part_pos[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    float*    part_spd[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    size_t    part_n[2]      = {0, 0};
+    int       part_cur[2]    = {0, 0}; // which buffer holds the current state
+    unsigned* part_finished  = nullptr; // particles parked by the last step (device counter)
     bool   skin_rot_set = false; // per-bone rotations supplied by the host instead of libm
     float  skin_rot[90];
 
@@ -913,8 +920,14 @@ void octree_cuc_destroy(octree_glc_t* rc)
     if (I->frame) cudaFree(I->frame);
     if (I->frame_alt) cudaFree(I->frame_alt);
     for (void* p : {(void*) I->skin_pos, (void*) I->skin_nrm, (void*) I->skin_p14, (void*) I->skin_p54,
-                    (void*) I->skin_p94, (void*) I->skin_pnt_out})
+                    (void*) I->skin_p94, (void*) I->skin_pnt_out, (void*) I->part_finished})
         if (p) cudaFree(p);
+    for (int k = 0; k < 2; k++)
+        for (int b = 0; b < 2; b++)
+        {
+            if (I->part_pos[k][b]) cudaFree(I->part_pos[k][b]);
+            if (I->part_spd[k][b]) cudaFree(I->part_spd[k][b]);
+        }
     if (I->ring_on)
     {
         cudaStreamSynchronize(I->copy_stream);
@@ -1661,6 +1674,95 @@ size_t octree_cuc_skeleton_read_out(octree_glc_t* rc, int32_t* oct14, int32_t* o
     }
     CUDA_OK(cudaStreamSynchronize(st));
     return n;
+}
+
+void octree_cuc_particles_alloc_in(octree_glc_t* rc, int kind, const float* posdata, const float* spddata, size_t bytes)
+{
+    Impl* I = impl_of(rc);
+    if (kind != OCTREE_CUC_PARTICLES && kind != OCTREE_CUC_DUST) die("particles_alloc_in: unknown kind");
+    const size_t n = bytes / 12;
+    CUDA_OK(cudaStreamSynchronize(I->stream));
+    if (n > I->part_n[kind] || !I->part_pos[kind][0])
+    {
+        for (int b = 0; b < 2; b++)
+        {
+            if (I->part_pos[kind][b]) CUDA_OK(cudaFree(I->part_pos[kind][b]));
+            if (I->part_spd[kind][b]) CUDA_OK(cudaFree(I->part_spd[kind][b]));
+            CUDA_OK(cudaMalloc(&I->part_pos[kind][b], (n ? n : 1) * 12));
+            CUDA_OK(cudaMalloc(&I->part_spd[kind][b], (n ? n : 1) * 12));
+        }
+        I->memsize += (n - I->part_n[kind]) * 48;
+        I->part_n[kind] = n;
+    }
+    if (!I->part_finished)
+    {
+        CUDA_OK(cudaMalloc(&I->part_finished, sizeof(unsigned)));
+        CUDA_OK(cudaMemsetAsync(I->part_finished, 0, sizeof(unsigned), I->stream));
+    }
+    I->part_cur[kind] = 0;
+    CUDA_OK(cudaMemcpyAsync(I->part_pos[kind][0], posdata, n * 12, cudaMemcpyHostToDevice, I->stream));
+    CUDA_OK(cudaMemcpyAsync(I->part_spd[kind][0], spddata, n * 12, cudaMemcpyHostToDevice, I->stream));
+    CUDA_OK(cudaStreamSynchronize(I->stream)); // the host arrays may change right after the call
+    publish_memsize(rc, I);
+}
+
+void octree_cuc_particles_update(octree_glc_t* rc, int kind, int count, int maxlevel, float basesize, v3_t campos,
+                                 int steps)
+{
+    Impl* I = impl_of(rc);
+    if (kind != OCTREE_CUC_PARTICLES && kind != OCTREE_CUC_DUST) die("particles_update: unknown kind");
+    if (count < 0 || (size_t) count > I->part_n[kind]) die("particles_update: more particles than particles_alloc_in gave");
+    if (maxlevel < 0 || maxlevel > GENERIC_STACK - 1) die("particles_update: maxlevel out of range");
+    if (count == 0 || steps <= 0) return;
+    flush_pending(I);
+    cudaStream_t st = I->stream;
+    FrameParams  P;
+    memset(&P, 0, sizeof(P));
+    P.tree_s.child = (const int4*) I->tree[0].child.ptr; // particle_glc.c L106-107: the static octree only
+    P.tree_s.model = (const int*) I->tree[0].model.ptr;
+    P.tree_s.nodes = (int) I->tree[0].nodes;
+    P.tree_d       = P.tree_s;
+    P.tree_d.nodes = 0;
+    P.basecube[0]  = 0.0f;
+    P.basecube[1] = P.basecube[2] = P.basecube[3] = basesize;
+    P.maxlevel                                    = maxlevel;
+    const size_t n = (size_t) count;
+    for (int s = 0; s < steps; s++)
+    {
+        const int a = I->part_cur[kind], b = a ^ 1;
+        if (kind == OCTREE_CUC_PARTICLES)
+        {
+            CUDA_OK(cudaMemsetAsync(I->part_finished, 0, sizeof(unsigned), st));
+            if (I->div_mode == DIV_GLSL)
+                particle_step_kernel<DIV_GLSL><<<nblk(n), 256, 0, st>>>(P, n, I->part_pos[kind][a], I->part_spd[kind][a],
+                                                                        I->part_pos[kind][b], I->part_spd[kind][b],
+                                                                        I->part_finished);
+            else
+                particle_step_kernel<DIV_IEEE><<<nblk(n), 256, 0, st>>>(P, n, I->part_pos[kind][a], I->part_spd[kind][a],
+                                                                        I->part_pos[kind][b], I->part_spd[kind][b],
+                                                                        I->part_finished);
+        }
+        else
+            dust_step_kernel<<<nblk(n), 256, 0, st>>>(make_float3(campos.x, campos.y, campos.z), n, I->part_pos[kind][a],
+                                                      I->part_spd[kind][a], I->part_pos[kind][b], I->part_spd[kind][b]);
+        CUDA_OK(cudaGetLastError());
+        I->launches++;
+        I->part_cur[kind] = b;
+    }
+}
+
+size_t octree_cuc_particles_read_out(octree_glc_t* rc, int kind, int count, float* pos_out, float* spd_out)
+{
+    Impl* I = impl_of(rc);
+    if (kind != OCTREE_CUC_PARTICLES && kind != OCTREE_CUC_DUST) die("particles_read_out: unknown kind");
+    if (count < 0 || (size_t) count > I->part_n[kind]) die("particles_read_out: count beyond particles_alloc_in");
+    const int a = I->part_cur[kind];
+    if (pos_out) CUDA_OK(cudaMemcpyAsync(pos_out, I->part_pos[kind][a], (size_t) count * 12, cudaMemcpyDeviceToHost, I->stream));
+    if (spd_out) CUDA_OK(cudaMemcpyAsync(spd_out, I->part_spd[kind][a], (size_t) count * 12, cudaMemcpyDeviceToHost, I->stream));
+    unsigned fin = 0;
+    if (I->part_finished) CUDA_OK(cudaMemcpyAsync(&fin, I->part_finished, sizeof(unsigned), cudaMemcpyDeviceToHost, I->stream));
+    CUDA_OK(cudaStreamSynchronize(I->stream));
+    return kind == OCTREE_CUC_PARTICLES ? (size_t) fin : 0;
 }
 
 void octree_cuc_trace_lines(octree_glc_t* rc, size_t n, const float* pos, const float* dir, int dynamic_tree,

@@ -68,7 +68,7 @@ __global__ void trace_lines_kernel(const FrameParams P, size_t n, const float* _
     size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
     if (i >= n) return;
     RayCounters       cnt;
-    const TraceResult r = trace_generic<DIV_IEEE, false, true>(P, make_float3(pos[i * 3], pos[i * 3 + 1], pos[i * 3 + 2]),
+    const TraceResult r = trace_generic<DIV_IEEE, false, TRACE_CPU>(P, make_float3(pos[i * 3], pos[i * 3 + 1], pos[i * 3 + 2]),
                                                                make_float3(dir[i * 3], dir[i * 3 + 1], dir[i * 3 + 2]), cnt);
     out_index[i]        = r.status == 1 ? r.model_s : 0;
     if (out_tlf && r.status == 1)

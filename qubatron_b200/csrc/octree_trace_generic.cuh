@@ -48,15 +48,33 @@ __device__ __forceinline__ float qdiv(float n, float d)
     return n / d;
 }
 
+// The traversal exists in three places of the reference with small, deliberate-or-not differences; TWIN selects whose
+// behaviour is reproduced:
+//   TRACE_FSH      the pixel program octree_fsh.c (the hot path)
+//   TRACE_CPU      the engine's CPU function octree_trace_line (octree.c L341-537)
+//   TRACE_PARTICLE the particle program particle_vsh.c L67-343 (static tree only)
+constexpr int TRACE_FSH      = 0;
+constexpr int TRACE_CPU      = 1;
+constexpr int TRACE_PARTICLE = 2;
+
+// parallel ray: the pixel program's sentinel is FLT_MAX in every component (octree_fsh.c L64); the CPU function
+// uses (0,0,0,FLT_MAX) (octree.c L304, L317, L330) and the particle program vec4(0.0) (particle_vsh.c L69, L82,
+// L95), whose xyz CAN pass a range test -- kept as they are
+template <int TWIN>
+__device__ __forceinline__ float4 parallel_sentinel()
+{
+    if (TWIN == TRACE_CPU) return make_float4(0.0f, 0.0f, 0.0f, FLT_MAX);
+    if (TWIN == TRACE_PARTICLE) return make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    return make_float4(FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX);
+}
+
 // ray / axis-plane intersection (octree_fsh.c L62-99): w = (c - o)/d, the other
 // two coordinates o + d*w, the plane coordinate exactly c.  A ray parallel to
 // the plane yields FLT_MAX in every component so all range tests fail.
-template <int DIV, bool TWIN = false>
+template <int DIV, int TWIN = 0>
 __device__ __forceinline__ float4 plane_hit_x(float c, float3 o, float3 d)
 {
-    // parallel ray: the shader's sentinel is FLT_MAX in every component (octree_fsh.c L64); the engine's CPU twin
-    // uses (0,0,0,FLT_MAX) (octree.c L304, L317, L330), whose xyz CAN pass a range test -- kept as it is
-    float4 r = TWIN ? make_float4(0.0f, 0.0f, 0.0f, FLT_MAX) : make_float4(FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX);
+    float4 r = parallel_sentinel<TWIN>();
     if (d.x != 0.0f)
     {
         r.w = qdiv<DIV>(c - o.x, d.x);
@@ -66,12 +84,10 @@ __device__ __forceinline__ float4 plane_hit_x(float c, float3 o, float3 d)
     }
     return r;
 }
-template <int DIV, bool TWIN = false>
+template <int DIV, int TWIN = 0>
 __device__ __forceinline__ float4 plane_hit_y(float c, float3 o, float3 d)
 {
-    // parallel ray: the shader's sentinel is FLT_MAX in every component (octree_fsh.c L64); the engine's CPU twin
-    // uses (0,0,0,FLT_MAX) (octree.c L304, L317, L330), whose xyz CAN pass a range test -- kept as it is
-    float4 r = TWIN ? make_float4(0.0f, 0.0f, 0.0f, FLT_MAX) : make_float4(FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX);
+    float4 r = parallel_sentinel<TWIN>();
     if (d.y != 0.0f)
     {
         r.w = qdiv<DIV>(c - o.y, d.y);
@@ -81,12 +97,10 @@ __device__ __forceinline__ float4 plane_hit_y(float c, float3 o, float3 d)
     }
     return r;
 }
-template <int DIV, bool TWIN = false>
+template <int DIV, int TWIN = 0>
 __device__ __forceinline__ float4 plane_hit_z(float c, float3 o, float3 d)
 {
-    // parallel ray: the shader's sentinel is FLT_MAX in every component (octree_fsh.c L64); the engine's CPU twin
-    // uses (0,0,0,FLT_MAX) (octree.c L304, L317, L330), whose xyz CAN pass a range test -- kept as it is
-    float4 r = TWIN ? make_float4(0.0f, 0.0f, 0.0f, FLT_MAX) : make_float4(FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX);
+    float4 r = parallel_sentinel<TWIN>();
     if (d.z != 0.0f)
     {
         r.w = qdiv<DIV>(c - o.z, d.z);
@@ -225,7 +239,7 @@ __device__ __forceinline__ bool base_cube_entry_q(const float* basecube, float3 
     return true;
 }
 
-template <int DIV, bool TWIN = false>
+template <int DIV, int TWIN = 0>
 __device__ __forceinline__ bool base_cube_entry(const float* basecube, float3 pos, float3 dir, float4& entry)
 {
     Cube c;
@@ -241,7 +255,7 @@ __device__ __forceinline__ bool base_cube_entry(const float* basecube, float3 po
 
 #define QB_FACE(ACT, COND)                                                                                            \
     act = ACT;                                                                                                        \
-    if ((!TWIN || act.w < FLT_MAX) && (COND)) /* octree.c L360-386 tests w < FLT_MAX on the six faces */            \
+    if ((TWIN != TRACE_CPU || act.w < FLT_MAX) && (COND)) /* octree.c L360-386: w < FLT_MAX on the six faces */     \
     {                                                                                                                 \
         if (hitc == 0) h0 = act;                                                                                      \
         if (hitc == 1) h1 = act;                                                                                      \
@@ -277,7 +291,7 @@ struct GenericLevel
 
 constexpr int GENERIC_STACK = 18; // octree_fsh.c L151
 
-template <int DIV, bool COUNT, bool TWIN = false>
+template <int DIV, bool COUNT, int TWIN = 0>
 __device__ __noinline__ TraceResult trace_generic(const FrameParams& P, float3 pos, float3 dir, RayCounters& cnt)
 {
     TraceResult res;
@@ -339,7 +353,11 @@ __device__ __noinline__ TraceResult trace_generic(const FrameParams& P, float3 p
         if (stck[level].ispsi == 0 || (stck[level].ispsi & 0x0F) != 0)
         {
             cs = load_children(P.tree_s, sn, level);
-            cd = load_children(P.tree_d, dn, level);
+            if (TWIN != TRACE_PARTICLE) cd = load_children(P.tree_d, dn, level);
+            // particle_vsh.c L108-119 addresses texel (3i mod 8192) + octi/4 of row 3i / 8192 WITHOUT wrapping into the
+            // next row (octree_fsh.c L130-135 wraps): for a node whose first texel is the last of its row, children
+            // 4..7 are fetched outside the texture and read 0
+            if (TWIN == TRACE_PARTICLE && ((3 * sn) & 8191) == 8191) cs.hi = make_int4(0, 0, 0, 0);
         }
 
         if (stck[level].ispsi == 0) // L251-330

@@ -45,3 +45,11 @@ def load_skin(name):
     """(positions, normals, golden dict) of a skinning fixture (tests/golden/make_golden_skin.py)."""
     i = np.load(os.path.join(GOLDEN, "skin_inputs.npz"))
     return i["positions"], i["normals"], np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+PARTICLE_CASES = ["particles_cloud", "particles_rowend"]
+
+
+def load_particles(name):
+    """golden dict of a particle / dust fixture (tests/golden/make_golden_particles.py)."""
+    return np.load(os.path.join(GOLDEN, name + ".npz"))

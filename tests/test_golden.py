@@ -55,3 +55,38 @@ def test_skin_oracle_equals_the_reference_vertex_program(name):
     assert (d2 != g["digits"]).any(axis=1).mean() < 0.01
     if name == "skin_rest":
         assert np.array_equal(d2, g["digits"]) and np.array_equal(pnt2.view(np.uint32), g["pnt"].view(np.uint32))
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+@pytest.mark.parametrize("name", golden_util.PARTICLE_CASES)
+def test_particle_oracle_equals_the_reference_vertex_program(name):
+    """oracle/particle_vsh_oracle.c against particle_vsh.c as llvmpipe ran it through transform feedback: positions
+    and speeds after one step and after `steps` chained steps are bit-identical, including the program's vec4(0.0)
+    parallel-ray result and its missing texture-row wrap (particles_rowend: a level-3 node at a row end hides the
+    half of a sheet that lies in its child slots 4..7)."""
+    g = golden_util.load_particles(name)
+    steps = int(g["steps"])
+    p, s = g["pos"], g["spd"]
+    for k in range(1, steps + 1):
+        p, s, hit = O.particles(g["oct_s"], p, s)
+        if k in (1, steps):
+            assert np.array_equal(_bits(p), _bits(g["pos_%d" % k])), k
+            assert np.array_equal(_bits(s), _bits(g["spd_%d" % k])), k
+    if name == "particles_rowend":
+        low = g["pos"][:, 2] < 1012.5
+        stuck = g["spd_1"][:, 0] < -900
+        assert stuck[low].sum() == 0 and stuck[~low].sum() > 1000
+
+
+def test_dust_oracle_equals_the_reference_vertex_program():
+    g = golden_util.load_particles("dust_box")
+    steps = int(g["steps"])
+    p, s = g["pos"], g["spd"]
+    for k in range(1, steps + 1):
+        p, s = O.dust(g["campos"], p, s)
+        if k in (1, steps):
+            assert np.array_equal(_bits(p), _bits(g["pos_%d" % k])), k
+            assert np.array_equal(_bits(s), _bits(g["spd_%d" % k])), k

@@ -575,6 +575,73 @@ def test_skin_build_render_on_the_device_equals_the_host_pipeline(scene_c1):
     rc.destroy()
 
 
+@pytest.mark.parametrize("name", __import__("golden_util").PARTICLE_CASES)
+def test_particle_step_equals_the_reference_vertex_program_on_llvmpipe(name):
+    """octree_cuc_particles_update ("next" row 8f #2) against particle_vsh.c itself (tests/golden, transform feedback
+    on llvmpipe): after one step and after `steps` steps kept on the device every position and speed is
+    bit-identical; the parked count equals the host's end-of-simulation test."""
+    import golden_util
+    g = golden_util.load_particles(name)
+    steps = int(g["steps"])
+    rc = K.OctreeGlc(b"", device=0)
+    rc.upload_octree(g["oct_s"])
+    rc.particles_alloc_in(g["pos"], g["spd"])
+    rc.particles_update(steps=1)
+    pos, spd, parked = rc.particles_read_out()
+    assert np.array_equal(pos.view(np.uint32), g["pos_1"].view(np.uint32))
+    assert np.array_equal(spd.view(np.uint32), g["spd_1"].view(np.uint32))
+    assert parked == int((g["spd_1"][:, 0] < -900).sum())
+    rc.particles_update(steps=steps - 1)
+    pos, spd, parked = rc.particles_read_out()
+    assert np.array_equal(pos.view(np.uint32), g["pos_%d" % steps].view(np.uint32))
+    assert np.array_equal(spd.view(np.uint32), g["spd_%d" % steps].view(np.uint32))
+    assert parked == int((g["spd_%d" % steps][:, 0] < -900).sum())
+    rc.destroy()
+
+
+@pytest.mark.parametrize("div", [K.DIV_GLSL, K.DIV_IEEE])
+def test_particle_step_equals_the_oracle(scene_c1, div):
+    """Debris over the C1 room (1.3 M-node static tree), both division modes, 8 chained steps, partial counts."""
+    rng = np.random.default_rng(17)
+    n = 50000
+    idx = rng.integers(0, len(scene_c1.pnt_s), n)
+    pos = (scene_c1.pnt_s[idx] + rng.normal(0, 5, (n, 3))).astype(np.float32)
+    spd = rng.normal(0, 2.5, (n, 3)).astype(np.float32)
+    spd[:1000, 0] = 0
+    spd[1000:2000, 1] = 0.4       # gravity makes it exactly 0: a ray parallel to the y planes
+    spd[2000:3000, 2] = 0
+    rc = K.OctreeGlc(b"", device=0)
+    rc.set_division(div)
+    rc.upload_octree(scene_c1.oct_s)
+    rc.particles_alloc_in(pos, spd)
+    rc.particles_update(steps=8, count=n - 777)
+    got_p, got_s, parked = rc.particles_read_out(count=n - 777)
+    p, s = pos[:n - 777], spd[:n - 777]
+    for _ in range(8):
+        p, s, hit = O.particles(scene_c1.oct_s, p, s, div=div)
+    assert np.array_equal(got_p.view(np.uint32), p.view(np.uint32))
+    assert np.array_equal(got_s.view(np.uint32), s.view(np.uint32))
+    assert parked == int((s[:, 0] < -900).sum()) and parked > 1000
+    rc.destroy()
+
+
+def test_dust_step_equals_the_reference_vertex_program_on_llvmpipe():
+    import golden_util
+    g = golden_util.load_particles("dust_box")
+    steps = int(g["steps"])
+    rc = K.OctreeGlc(b"", device=0)
+    rc.particles_alloc_in(g["pos"], g["spd"], kind=K.DUST)
+    rc.particles_update(kind=K.DUST, campos=tuple(g["campos"]), steps=1)
+    pos, spd, _ = rc.particles_read_out(kind=K.DUST)
+    assert np.array_equal(pos.view(np.uint32), g["pos_1"].view(np.uint32))
+    assert np.array_equal(spd.view(np.uint32), g["spd_1"].view(np.uint32))
+    rc.particles_update(kind=K.DUST, campos=tuple(g["campos"]), steps=steps - 1)
+    pos, spd, _ = rc.particles_read_out(kind=K.DUST)
+    assert np.array_equal(pos.view(np.uint32), g["pos_%d" % steps].view(np.uint32))
+    assert np.array_equal(spd.view(np.uint32), g["spd_%d" % steps].view(np.uint32))
+    rc.destroy()
+
+
 def test_gpu_voxelise_and_bulk_build_equal_the_host_model():
     """octree_cuc_voxelise_and_build ("next" row 8f #3): the same survivors in the same order as the qmc rules
     (host voxeliser, itself byte-identical to the reference qmc binary in tests/test_host_model.py), the same
