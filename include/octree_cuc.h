@@ -261,6 +261,18 @@ size_t octree_cuc_skeleton_update(octree_glc_t* rc, const float* oldbones80, con
 size_t octree_cuc_skeleton_read_out(octree_glc_t* rc, int32_t* oct14, int32_t* oct54, int32_t* oct94, float* nrm_out,
                                     float* pnt_out);
 
+/* "Next" row (second half): the presentation pass of octree_glc_update (octree_glc.c L308-351).  With
+ * present enabled every single-view, unsharded octree_glc_update also produces what the reference leaves in the
+ * window's back buffer: the frame drawn LINEAR-filtered into (int)width x (int)height pixels (all four channels),
+ * plus the 2 x 2 white crosshair.  The window image stays on the device (octree_cuc_window_device: RGBA8, row 0 =
+ * bottom -- what an interactive build registers with its window texture) or is copied out (octree_cuc_read_window,
+ * which also reports the size; returns bytes copied or 0).  Off by default: the bench measures the frame.
+ * Filter precision is implementation-defined in GL; the connector reproduces Mesa llvmpipe's RGBA8 filter bit for
+ * bit (8-bit weights, like NVIDIA hardware); at quality 10 the pass is an exact copy on any implementation. */
+void     octree_cuc_enable_present(octree_glc_t* rc, int on);
+size_t   octree_cuc_read_window(octree_glc_t* rc, uint8_t* rgba_host, size_t capacity, int* width, int* height);
+uint64_t octree_cuc_window_device(octree_glc_t* rc);
+
 /* "Next" row: the particle and dust simulation steps of the reference's transform-feedback programs
  * (shaders/particle_vsh.c dispatched by particle_glc.c L118-156 over the octree texture that octree_glc.c bound,
  * L105-113; shaders/dust_vsh.c dispatched by dust_glc.c L103-135).  `kind` selects the program.

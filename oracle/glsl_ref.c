@@ -24,6 +24,8 @@
  *   mode 3 : aux dump of the shadow visibility step(sqr, 15.0)
  *   The aux modes append statements that copy a value to the output; the traversal
  *   and shading code is untouched.
+ *   mode 40 : mode 0 followed by the presentation pass (texquad shaders + crosshair) into a $QB_WINDOW = WxH window;
+ *             the output is the window image
  *   mode 20 - 22 : skeleton_vsh.c through transform feedback (see skin_main below)
  *   mode 30 / 31 : particle_vsh.c / dust_vsh.c through transform feedback (see particle_main below)
  * prints one JSON line with renderer, version and per-frame seconds.
@@ -39,6 +41,8 @@
 
 extern const char _binary_octree_fsh_c_start[], _binary_octree_fsh_c_end[];
 extern const char _binary_octree_vsh_c_start[], _binary_octree_vsh_c_end[];
+extern const char _binary_texquad_vsh_c_start[], _binary_texquad_vsh_c_end[];
+extern const char _binary_texquad_fsh_c_start[], _binary_texquad_fsh_c_end[];
 extern const char _binary_skeleton_vsh_c_start[], _binary_skeleton_vsh_c_end[];
 extern const char _binary_skeleton_fsh_c_start[], _binary_skeleton_fsh_c_end[];
 extern const char _binary_particle_vsh_c_start[], _binary_particle_vsh_c_end[];
@@ -87,6 +91,7 @@ typedef long         GLsizeiptr;
 #define GL_VERSION 0x1F02
 #define GL_PACK_ALIGNMENT 0x0D05
 #define GL_POINTS 0
+#define GL_SCISSOR_TEST 0x0C11
 #define GL_STATIC_DRAW 0x88E4
 #define GL_STREAM_READ 0x88E1
 #define GL_RASTERIZER_DISCARD 0x8C89
@@ -148,6 +153,8 @@ GLFN(const unsigned char*, glGetString, GLenum)
 GLFN(GLenum, glGetError, void)
 GLFN(void, glEnable, GLenum)
 GLFN(void, glPixelStorei, GLenum, GLint)
+GLFN(void, glScissor, GLint, GLint, GLsizei, GLsizei)
+GLFN(void, glDisable, GLenum)
 GLFN(void, glTransformFeedbackVaryings, GLuint, GLsizei, const GLchar* const*, GLenum)
 GLFN(void, glBindBufferBase, GLenum, GLuint, GLuint)
 GLFN(void, glBeginTransformFeedback, GLenum)
@@ -249,7 +256,9 @@ static void gl_context(void)
     if (!gl) die(dlerror());
 
     void* (*open_display)(int, int) = need(x11, "qb_stub_open_display");
-    void* dpy                       = open_display(64, 64);
+    int win_w = 64, win_h = 64; /* the default framebuffer; mode 40 presents into it */
+    if (getenv("QB_WINDOW")) sscanf(getenv("QB_WINDOW"), "%dx%d", &win_w, &win_h);
+    void* dpy = open_display(win_w, win_h);
 
     void* (*glXChooseVisual)(void*, int, int*)        = need(gl, "glXChooseVisual");
     void* (*glXCreateContext)(void*, void*, void*, int) = need(gl, "glXCreateContext");
@@ -273,7 +282,7 @@ static void gl_context(void)
     LOAD(glFramebufferTexture2D) LOAD(glCheckFramebufferStatus) LOAD(glViewport) LOAD(glClearColor) LOAD(glClear)
     LOAD(glGenBuffers) LOAD(glBindBuffer) LOAD(glBufferData) LOAD(glGenVertexArrays) LOAD(glBindVertexArray)
     LOAD(glEnableVertexAttribArray) LOAD(glVertexAttribPointer) LOAD(glDrawArrays) LOAD(glFinish) LOAD(glReadPixels)
-    LOAD(glGetString) LOAD(glGetError) LOAD(glEnable) LOAD(glPixelStorei) LOAD(glTransformFeedbackVaryings)
+    LOAD(glGetString) LOAD(glGetError) LOAD(glEnable) LOAD(glPixelStorei) LOAD(glScissor) LOAD(glDisable) LOAD(glTransformFeedbackVaryings)
     LOAD(glBindBufferBase) LOAD(glBeginTransformFeedback) LOAD(glEndTransformFeedback) LOAD(glGetBufferSubData)
 }
 
@@ -569,7 +578,7 @@ int main(int argc, char** argv)
     const char* pack = "{ int qv = floatBitsToInt(qb_keep); fragColor = vec4(float(qv & 255) / 255.0, "
                        "float((qv >> 8) & 255) / 255.0, float((qv >> 16) & 255) / 255.0, "
                        "float((qv >> 24) & 255) / 255.0); }";
-    if (mode != 0)
+    if (mode != 0 && mode != 40)
     {
         /* qb_out is written at the leaf of whichever trace ran last; qb_keep latches the PRIMARY trace's value */
         fsh = patch(fsh, "out vec4 fragColor;",
@@ -690,6 +699,53 @@ int main(int argc, char** argv)
     }
     printf("], \"gl_error\": %u}\n", glGetError());
 
+    if (mode == 40)
+    {
+        /* ---- presentation, octree_glc.c L308-351: the render target drawn as a textured quad (texquad_vsh.c /
+         * texquad_fsh.c, LINEAR filter) into the window, then the 2 x 2 crosshair ---- */
+        int ww = 64, wh = 64;
+        if (getenv("QB_WINDOW")) sscanf(getenv("QB_WINDOW"), "%dx%d", &ww, &wh);
+        GLuint tq = glCreateProgram();
+        glAttachShader(tq, compile(GL_VERTEX_SHADER, embedded(_binary_texquad_vsh_c_start, _binary_texquad_vsh_c_end)));
+        glAttachShader(tq, compile(GL_FRAGMENT_SHADER, embedded(_binary_texquad_fsh_c_start, _binary_texquad_fsh_c_end)));
+        glBindAttribLocation(tq, 0, "position");
+        glBindAttribLocation(tq, 1, "texcoord");
+        glLinkProgram(tq);
+        glGetProgramiv(tq, GL_LINK_STATUS, &ok);
+        if (!ok) die("texquad link failed");
+        glBindFramebuffer(GL_FRAMEBUFFER, 0);
+        glClearColor(0.0f, 0.0f, 0.0f, 1.0f);
+        glClear(GL_COLOR_BUFFER_BIT | GL_DEPTH_BUFFER_BIT);
+        glUseProgram(tq);
+        glViewport(0, 0, ww, wh);
+        glUniformMatrix4fv(glGetUniformLocation(tq, "projection"), 1, 0, proj);
+        glActiveTexture(GL_TEXTURE0);
+        glUniform1i(glGetUniformLocation(tq, "texture_base"), 0);
+        glBindTexture(GL_TEXTURE_2D, rt);
+        GLfloat vq[] = {0.0f,    0.0f,    0.0f, 0.0f, 0.0f, 2048.0f, 0.0f,    0.0f, 1.0f, 0.0f,
+                        0.0f,    2048.0f, 0.0f, 0.0f, 1.0f, 0.0f,    2048.0f, 0.0f, 0.0f, 1.0f,
+                        2048.0f, 0.0f,    0.0f, 1.0f, 0.0f, 2048.0f, 2048.0f, 0.0f, 1.0f, 1.0f};
+        GLuint qvbo, qvao;
+        glGenBuffers(1, &qvbo);
+        glBindBuffer(GL_ARRAY_BUFFER, qvbo);
+        glGenVertexArrays(1, &qvao);
+        glBindVertexArray(qvao);
+        glEnableVertexAttribArray(0);
+        glEnableVertexAttribArray(1);
+        glVertexAttribPointer(0, 3, GL_FLOAT, 0, sizeof(GLfloat) * 5, 0);
+        glVertexAttribPointer(1, 2, GL_FLOAT, 0, sizeof(GLfloat) * 5, (const void*) 12);
+        glBufferData(GL_ARRAY_BUFFER, sizeof(vq), vq, GL_DYNAMIC_DRAW);
+        glDrawArrays(GL_TRIANGLES, 0, 6);
+        if (getenv("QB_NO_CROSSHAIR")) goto skip_crosshair;
+        glEnable(GL_SCISSOR_TEST);
+        glClearColor(1.0f, 1.0f, 1.0f, 1.0f);
+        glScissor(ww / 2 - 1, wh / 2 - 1, 2, 2);
+        glClear(GL_COLOR_BUFFER_BIT);
+        glDisable(GL_SCISSOR_TEST);
+    skip_crosshair:
+        glFinish();
+        W = ww, H = wh;
+    }
     unsigned char* out = malloc((size_t) W * H * 4);
     glReadPixels(0, 0, W, H, GL_RGBA, GL_UNSIGNED_BYTE, out);
     f = fopen(argv[2], "wb");

@@ -78,6 +78,7 @@ def lib(div=DIV_GLSL):
         l.qb_oracle_bone_rotations.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         l.qb_oracle_particles.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int64, C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        l.qb_oracle_present.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p]
         l.qb_oracle_dust.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _libs[div] = l
     return _libs[div]
@@ -195,6 +196,15 @@ def dust(campos, pos, spd, div=DIV_GLSL):
     return po, so
 
 
+def present(frame, u, width, height):
+    """octree_glc.c L308-351: the window image (uint8 [height,width,4]) of a rendered frame (uint8 [vp_h,vp_w,4])."""
+    frame = np.ascontiguousarray(frame, dtype=np.uint8)
+    out = np.zeros((int(height), int(width), 4), dtype=np.uint8)
+    lib(DIV_GLSL).qb_oracle_present(_ptr(frame), frame.shape[1], frame.shape[0], float(u.dimensions[0]),
+                                    float(u.dimensions[1]), int(width), int(height), _ptr(out))
+    return out
+
+
 def pixel_rays(u):
     """Primary ray direction of every pixel: float32 [H,W,3]."""
     W, H = u.vp_w, u.vp_h
@@ -303,7 +313,7 @@ def have_glsl():
                        "/opt/nvidia/nsight-compute/2025.2.1/host/linux-desktop-glibc_2_11_3-x64/Mesa/libGL.so.1"))
 
 
-def glsl_render(scene, u, mode=0, repeat=1, threads=None, workdir=None):
+def glsl_render(scene, u, mode=0, repeat=1, threads=None, workdir=None, window=None):
     """Run the reference shader for the uniforms `u`; returns (uint8 [H,W,4], info dict).
     mode 0 = shader as shipped; 1/2/3 = aux dumps (static model index, dynamic model index, shadow bit)
     returned as int32 [H,W] decoded from the RGBA8 bytes."""
@@ -329,13 +339,16 @@ def glsl_render(scene, u, mode=0, repeat=1, threads=None, workdir=None):
         env = dict(os.environ)
         if threads is not None:
             env["LP_NUM_THREADS"] = str(int(threads))
+        if window is not None:   # mode 40: present into a window of this size
+            env["QB_WINDOW"] = "%dx%d" % tuple(window)
+            W, H = window
         r = subprocess.run([REF_GLSL, fin, fout, str(mode), str(repeat)], stdout=subprocess.PIPE,
                            stderr=subprocess.PIPE, text=True, env=env)
         if r.returncode != 0:
             raise RuntimeError("glsl_ref failed (%d): %s" % (r.returncode, r.stderr[-2000:]))
         info = json.loads(r.stdout.strip().splitlines()[-1])
         out = np.fromfile(fout, dtype=np.uint8).reshape(H, W, 4)
-    if mode != 0:
+    if mode not in (0, 40):
         out = out.view(np.int32).reshape(H, W)
     return out, info
 

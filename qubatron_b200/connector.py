@@ -90,6 +90,10 @@ _PROTOS = {
                                                 C.c_float, C.c_int]),
     "octree_cuc_skeleton_read_out": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_void_p, C.c_void_p, C.c_void_p,
                                                   C.c_void_p, C.c_void_p]),
+    "octree_cuc_enable_present": (None, [C.POINTER(octree_glc_t), C.c_int]),
+    "octree_cuc_read_window": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_void_p, C.c_size_t, C.POINTER(C.c_int),
+                                            C.POINTER(C.c_int)]),
+    "octree_cuc_window_device": (C.c_uint64, [C.POINTER(octree_glc_t)]),
     "octree_cuc_particles_alloc_in": (None, [C.POINTER(octree_glc_t), C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
     "octree_cuc_particles_update": (None, [C.POINTER(octree_glc_t), C.c_int, C.c_int, C.c_int, C.c_float, v3_t,
                                            C.c_int]),
@@ -347,6 +351,22 @@ class OctreeGlc:
                                               p94.ctypes.data_as(C.c_void_p), nrm.ctypes.data_as(C.c_void_p),
                                               pnt.ctypes.data_as(C.c_void_p))
         return np.concatenate([p14, p54, p94], axis=1), nrm, pnt
+
+    def enable_present(self, on=True):
+        self.lib.octree_cuc_enable_present(self._p, int(bool(on)))
+
+    def read_window(self):
+        """The window image of the last update (uint8 [height,width,4], row 0 = bottom); needs enable_present."""
+        w, h = C.c_int(0), C.c_int(0)
+        self.lib.octree_cuc_read_window(self._p, None, 0, C.byref(w), C.byref(h))
+        out = np.zeros((h.value, w.value, 4), dtype=np.uint8)
+        if out.size:
+            got = self.lib.octree_cuc_read_window(self._p, out.ctypes.data_as(C.c_void_p), out.nbytes, None, None)
+            assert got == out.nbytes
+        return out
+
+    def window_device(self):
+        return int(self.lib.octree_cuc_window_device(self._p))
 
     def particles_alloc_in(self, pos, spd, kind=PARTICLES):
         pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 3)

@@ -12,6 +12,7 @@
 #include "octree_trace_fast.cuh"
 #include "skeleton_skin.cuh"
 #include "particle_sim.cuh"
+#include "present.cuh"
 
 #include <chrono>
 #include <cmath>
@@ -271,6 +272,11 @@ struct Impl
     int4 * skin_p14 = nullptr, *skin_p54 = nullptr, *skin_p94 = nullptr;
     float* skin_pnt_out = nullptr;
     size_t skin_count   = 0; // points of the last update
+    // presentation ("next" row 8f #4b): the window image of the last frame
+    bool    present_on  = false;
+    uchar4* window      = nullptr;
+    size_t  window_cap  = 0;
+    int     window_w = 0, window_h = 0;
     // particle / dust simulation state ("next" row 8f #2): [kind][in, out] position and speed, ping-pong
     float*    part_pos[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
     float*    part_spd[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
@@ -830,6 +836,41 @@ void render_views(octree_glc_t* rc, int n, float width, float height, const floa
         I->last_kernel = fast ? 2 : 1;
     }
     CUDA_OK(cudaEventRecord(I->ev1, I->stream));
+    if (I->present_on && n == 1 && I->shard_world == 1) // octree_glc.c L308-351; after ev1: not part of the frame time
+    {
+        const int ww = (int) width, wh = (int) height;
+        if (ww > 0 && wh > 0)
+        {
+            if ((size_t) ww * wh > I->window_cap)
+            {
+                if (I->window)
+                {
+                    CUDA_OK(cudaStreamSynchronize(I->stream));
+                    CUDA_OK(cudaFree(I->window));
+                    I->memsize -= I->window_cap * 4;
+                }
+                CUDA_OK(cudaMalloc(&I->window, (size_t) ww * wh * 4));
+                I->window_cap = (size_t) ww * wh;
+                I->memsize += I->window_cap * 4;
+            }
+            PresentParams Q;
+            Q.frame  = P.frame;
+            Q.pitch  = P.pitch;
+            Q.vp_w   = W;
+            Q.vp_h   = H;
+            Q.sx     = (double) ow / (double) ww;
+            Q.sy     = (double) oh / (double) wh;
+            Q.width  = ww;
+            Q.height = wh;
+            Q.window = I->window;
+            const dim3 blk(32, 8), grd((ww + 31) / 32, (wh + 7) / 8);
+            present_kernel<<<grd, blk, 0, I->stream>>>(Q);
+            CUDA_OK(cudaGetLastError());
+            I->launches++;
+            I->window_w = ww;
+            I->window_h = wh;
+        }
+    }
     if (I->ring_on && !I->ext_target) CUDA_OK(cudaEventRecord(I->ev_render[I->ring_cur], I->stream));
     I->timed = true;
     publish_memsize(rc, I);
@@ -919,6 +960,7 @@ void octree_cuc_destroy(octree_glc_t* rc)
     cudaFree(I->counters);
     if (I->frame) cudaFree(I->frame);
     if (I->frame_alt) cudaFree(I->frame_alt);
+    if (I->window) cudaFree(I->window);
     for (void* p : {(void*) I->skin_pos, (void*) I->skin_nrm, (void*) I->skin_p14, (void*) I->skin_p54,
                     (void*) I->skin_p94, (void*) I->skin_pnt_out, (void*) I->part_finished})
         if (p) cudaFree(p);
@@ -1030,6 +1072,22 @@ size_t octree_cuc_read_frame(octree_glc_t* rc, uint8_t* rgba_host, size_t capaci
     CUDA_OK(cudaStreamSynchronize(I->stream));
     return bytes;
 }
+
+void octree_cuc_enable_present(octree_glc_t* rc, int on) { impl_of(rc)->present_on = on != 0; }
+
+size_t octree_cuc_read_window(octree_glc_t* rc, uint8_t* rgba_host, size_t capacity, int* width, int* height)
+{
+    Impl*        I     = impl_of(rc);
+    const size_t bytes = (size_t) I->window_w * I->window_h * 4;
+    if (width) *width = I->window_w;
+    if (height) *height = I->window_h;
+    if (!rgba_host || bytes == 0 || capacity < bytes) return 0;
+    CUDA_OK(cudaMemcpyAsync(rgba_host, I->window, bytes, cudaMemcpyDeviceToHost, I->stream));
+    CUDA_OK(cudaStreamSynchronize(I->stream));
+    return bytes;
+}
+
+uint64_t octree_cuc_window_device(octree_glc_t* rc) { return (uint64_t) (uintptr_t) impl_of(rc)->window; }
 
 uint64_t octree_cuc_frame_device(octree_glc_t* rc)
 {

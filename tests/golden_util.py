@@ -53,3 +53,13 @@ PARTICLE_CASES = ["particles_cloud", "particles_rowend"]
 def load_particles(name):
     """golden dict of a particle / dust fixture (tests/golden/make_golden_particles.py)."""
     return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+PRESENT_QUALITIES = [10, 9, 8, 7, 6, 5, 4]
+
+
+def load_present(q):
+    """(scene, args, golden) of a presentation fixture (tests/golden/make_golden_present.py); scene = cloud_a's."""
+    sc, _, _ = load("cloud_a")
+    g = np.load(os.path.join(GOLDEN, "present_q%d.npz" % q))
+    return sc, ast.literal_eval(str(g["args"])), g

@@ -90,3 +90,20 @@ def test_dust_oracle_equals_the_reference_vertex_program():
         if k in (1, steps):
             assert np.array_equal(_bits(p), _bits(g["pos_%d" % k])), k
             assert np.array_equal(_bits(s), _bits(g["spd_%d" % k])), k
+
+
+@pytest.mark.parametrize("q", golden_util.PRESENT_QUALITIES)
+def test_present_oracle_equals_the_reference_window(q):
+    """oracle/present_oracle.c against the window image of the reference's full octree_glc_update on llvmpipe
+    (octree_glc.c L308-351: LINEAR-filtered textured quad + crosshair): every pixel, all four channels, at every
+    render scale the engine offers; the oracle's own frame (RGB within 1/255 of the shader's) presents to within 1."""
+    sc, args, g = golden_util.load_present(q)
+    u = O.uniforms(**args)
+    assert g["frame"].shape[:2] == (u.vp_h, u.vp_w)
+    win = O.present(g["frame"], u, args["width"], args["height"])
+    assert np.array_equal(win, g["window"])
+    r = O.render(O.OracleScene(sc), u)
+    own = O.present(r["rgba"], u, args["width"], args["height"])   # the oracle's frame is within +-1 of the shader's
+    assert np.abs(own.astype(int) - g["window"].astype(int)).max() <= 1
+    cy, cx = args["height"] // 2, args["width"] // 2
+    assert (g["window"][cy - 1:cy + 1, cx - 1:cx + 1] == 255).all()

@@ -642,6 +642,49 @@ def test_dust_step_equals_the_reference_vertex_program_on_llvmpipe():
     rc.destroy()
 
 
+@pytest.mark.parametrize("q", __import__("golden_util").PRESENT_QUALITIES)
+def test_presentation_pass_equals_the_reference_window_on_llvmpipe(q):
+    """octree_glc_update with presentation enabled ("next" row 8f #4b) against the window image the reference's own
+    octree_glc_update leaves behind on llvmpipe (render target -> LINEAR-filtered quad -> crosshair), at every render
+    scale, for both kernels: the pass is bit-exact given the frame; the frame is within the renderer's 1/255."""
+    import golden_util
+    sc, args, g = golden_util.load_present(q)
+    rc = K.OctreeGlc(b"", device=0)
+    rc.upload_scene(sc)
+    rc.enable_present(True)
+    for kern, name in KERNELS:
+        rc.set_kernel(kern)
+        rc.update(args["width"], args["height"], args["position"], args["angle"], quality=args["quality"],
+                  shoot=args["shoot"])
+        frame = rc.read_frame()
+        assert np.abs(frame.astype(int) - g["frame"].astype(int)).max() <= parity.RGB_TOL, name
+        win = rc.read_window()
+        assert win.shape == g["window"].shape
+        # the pass itself is exact: presenting the connector's own frame with the pinned oracle gives the same bytes
+        assert np.array_equal(win, O.present(frame, O.uniforms(**args), args["width"], args["height"])), name
+        if np.array_equal(frame, g["frame"]):
+            assert np.array_equal(win, g["window"]), name
+        assert np.abs(win.astype(int) - g["window"].astype(int)).max() <= parity.RGB_TOL, name
+    rc.enable_present(False)
+    rc.destroy()
+
+
+def test_presentation_at_full_size_equals_the_oracle(scene_c1):
+    """1080p window at quality 10 (a copy + crosshair) and at quality 7 (2.5x upscale of a 768 x 432 frame)."""
+    rc = K.OctreeGlc(b"", device=0)
+    rc.upload_scene(scene_c1)
+    rc.enable_present(True)
+    osc = O.OracleScene(scene_c1)
+    for quality in (10, 7):
+        rc.update(1920, 1080, *S.CAMERA_C1, quality=quality)
+        u = O.uniforms(1920, 1080, *S.CAMERA_C1, quality=quality)
+        frame = rc.read_frame()
+        assert np.array_equal(rc.read_window(), O.present(frame, u, 1920, 1080))
+        r = O.render(osc, u)
+        assert np.abs(frame.astype(int) - r["rgba"].astype(int)).max() <= parity.RGB_TOL
+    rc.destroy()
+
+
 def test_gpu_voxelise_and_bulk_build_equal_the_host_model():
     """octree_cuc_voxelise_and_build ("next" row 8f #3): the same survivors in the same order as the qmc rules
     (host voxeliser, itself byte-identical to the reference qmc binary in tests/test_host_model.py), the same
