@@ -603,6 +603,19 @@ int main(int argc, char** argv)
                  getenv("QB_DEBUG_EXPR") ? getenv("QB_DEBUG_EXPR") : "csv.x");
         fsh = patch(fsh, "csv = quat_rotate(qx, csv);", buf);
     }
+    if (mode == 7) /* debug: patch QB_PATCH_NEEDLE -> QB_PATCH_REPL anywhere (e.g. qb_out = ...), dump QB_DEBUG_EXPR at the end */
+    {
+        char buf[512];
+        if (getenv("QB_PATCH_NEEDLE")) fsh = patch(fsh, getenv("QB_PATCH_NEEDLE"), getenv("QB_PATCH_REPL"));
+        snprintf(buf, sizeof(buf), "col.z *= 0.7;\nqb_keep = %s;", getenv("QB_DEBUG_EXPR") ? getenv("QB_DEBUG_EXPR") : "qb_out");
+        fsh = patch(fsh, "col.z *= 0.7;", buf);
+    }
+    if (mode == 8) /* debug: any float expression of main() evaluated after the shading (QB_DEBUG_EXPR) */
+    {
+        char buf[512];
+        snprintf(buf, sizeof(buf), "col.z *= 0.7;\nqb_keep = %s;", getenv("QB_DEBUG_EXPR") ? getenv("QB_DEBUG_EXPR") : "sqr");
+        fsh = patch(fsh, "col.z *= 0.7;", buf);
+    }
     if (mode == 3)
         fsh = patch(fsh, "col.z *= 0.7;", "col.z *= 0.7;\nqb_keep = intBitsToFloat(int(step(sqr, 15.0)));");
 

@@ -19,6 +19,7 @@
 
 #include <float.h>
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -292,6 +293,10 @@ static trace_res trace_line(const qb_scene* sc, const qb_uniforms* u, f3 pos, f3
                 if (act.x > hlf.x) oct = 1;
                 if (act.y < hlf.y) oct += 2;
                 if (act.z < hlf.z) oct += 4;
+#ifdef QB_ORACLE_DEBUG
+                fprintf(stderr, "L%d tlf %a %a %a %a hlf %a %a %a  cand %d/%d: %a %a %a w %a oct %d pre %d\n", level, tlf.x,
+                        tlf.y, tlf.z, tlf.w, hlf.x, hlf.y, hlf.z, i, hc, act.x, act.y, act.z, act.w, oct, pre);
+#endif
 
                 if (oct == pre)
                 {

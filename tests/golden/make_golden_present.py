@@ -23,7 +23,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 import golden_util  # noqa: E402
 from oracle import qb_oracle as O  # noqa: E402
 
-CASES = {10: (192, 108), 9: (300, 170), 8: (400, 226), 7: (600, 340), 6: (501, 333), 5: (700, 394), 4: (512, 288)}
+CASES = {10: (192, 108), 9: (300, 170), 8: (400, 226), 7: (480, 270), 6: (501, 333), 5: (700, 394), 4: (512, 288)}
 
 if __name__ == "__main__":
     O.build(ref=True)
