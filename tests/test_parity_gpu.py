@@ -364,7 +364,7 @@ def test_c_host_demo():
     r = subprocess.run([os.path.join(ex, "host_demo")], cwd=ex, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
                        text=True, timeout=120)
     assert r.returncode == 0, r.stdout
-    assert "leaf pixels" in r.stdout
+    assert "leaf pixels" in r.stdout and "dynamic pipeline" in r.stdout
 
 
 def test_dynamic_tree_rebuilt_every_frame(scene_c1):
