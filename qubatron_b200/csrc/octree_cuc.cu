@@ -1317,8 +1317,9 @@ extern "C" {
 namespace
 {
 // paths on the device -> tree `t` in the traversal layout; returns the node count
+// keys_ready: optional scratch buffer of n sort words already filled by the producer (skin kernel); taken over
 size_t build_from_device_paths(Impl* I, int buftype, const int* p14, const int* p54, const int* p94, size_t n,
-                               int first_modind, int levels)
+                               int first_modind, int levels, unsigned long long* keys_ready = nullptr)
 {
     const int    t  = tree_index(buftype);
     cudaStream_t st = I->stream;
@@ -1331,10 +1332,11 @@ size_t build_from_device_paths(Impl* I, int buftype, const int* p14, const int* 
         using u64 = unsigned long long;
         // 1. one word per point (path << 28 | index) sorted on the path bits; the first word of every distinct path
         //    carries the smallest index
-        u64* keys_a = scratch<u64>(I, n);
+        u64* keys_a = keys_ready ? keys_ready : scratch<u64>(I, n);
         u64* keys_b = scratch<u64>(I, n);
-        build_key_kernel<<<nblk(n), 256, 0, st>>>((const int4*) p14, (const int4*) p54, (const int4*) p94, n, levels,
-                                                  keys_a);
+        if (!keys_ready)
+            build_key_kernel<<<nblk(n), 256, 0, st>>>((const int4*) p14, (const int4*) p54, (const int4*) p94, n, levels,
+                                                      keys_a);
         size_t tb = 0;
         CUDA_OK(cub::DeviceRadixSort::SortKeys(nullptr, tb, keys_a, keys_b, (int) n, BUILD_INDEX_BITS,
                                                BUILD_INDEX_BITS + 3 * levels, st));
@@ -1363,16 +1365,19 @@ size_t build_from_device_paths(Impl* I, int buftype, const int* p14, const int* 
         int*           parent_leaf = scratch<int>(I, (size_t) U);
         build_leafinfo_kernel<<<nblk(U), 256, 0, st>>>(K, U, levels, first_diff, created);
         tb = 0;
-        CUDA_OK(cub::DeviceScan::ExclusiveSum(nullptr, tb, created, base, U, st));
+        CUDA_OK(cub::DeviceScan::ExclusiveSum(nullptr, tb, (const unsigned*) created, (unsigned*) base, U, st));
         tmp = scratch<char>(I, tb);
-        CUDA_OK(cub::DeviceScan::ExclusiveSum(tmp, tb, created, base, U, st));
+        CUDA_OK(cub::DeviceScan::ExclusiveSum(tmp, tb, (const unsigned*) created, (unsigned*) base, U, st));
         scratch_free(I, tmp);
         build_parent_kernel<<<nblk(U), 256, 0, st>>>(K, U, levels, first_diff, parent_leaf);
-        int last[2] = {0, 0};
+        unsigned last[2] = {0, 0};
         CUDA_OK(cudaMemcpyAsync(&last[0], base + (U - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
         CUDA_OK(cudaMemcpyAsync(&last[1], created + (U - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
         CUDA_OK(cudaStreamSynchronize(st));
-        total = 1 + last[0] + last[1];
+        // the scan ran in unsigned arithmetic (at most 12 * 2^28 < 2^32); the node format holds 2^28 nodes
+        const unsigned long long all_nodes = 1ull + last[0] + last[1];
+        if (all_nodes >= (1ull << 28)) die("build_octree_from_paths: the tree would exceed 2^28 nodes");
+        total = (int) all_nodes;
 
         // 3. creators and child tables, leaves upwards
         tmp_child    = scratch<int>(I, (size_t) total * 8);
@@ -1396,6 +1401,7 @@ size_t build_from_device_paths(Impl* I, int buftype, const int* p14, const int* 
     }
     else
     {
+        if (keys_ready) scratch_free(I, keys_ready);
         tmp_child = scratch<int>(I, 8);
         tmp_key   = scratch<unsigned>(I, 1);
         CUDA_OK(cudaMemsetAsync(tmp_child, 0, 8 * sizeof(int), st));
@@ -1684,15 +1690,16 @@ size_t octree_cuc_skeleton_update(octree_glc_t* rc, const float* oldbones80, con
     S.maxlevel = maxlevel;
     const size_t n = (size_t) model_count;
     size_t       nodes = 0;
+    unsigned long long* keys = (build_tree && n) ? scratch<unsigned long long>(I, n) : nullptr;
     if (n)
     {
         float* rec = (float*) I->pts[1].rec.ptr;
         if (I->div_mode == DIV_GLSL)
             skin_kernel<DIV_GLSL><<<nblk(n), 256, 0, I->stream>>>(S, n, I->skin_pos, I->skin_nrm, I->skin_p14,
-                                                                  I->skin_p54, I->skin_p94, rec, I->skin_pnt_out);
+                                                                  I->skin_p54, I->skin_p94, rec, I->skin_pnt_out, keys);
         else
             skin_kernel<DIV_IEEE><<<nblk(n), 256, 0, I->stream>>>(S, n, I->skin_pos, I->skin_nrm, I->skin_p14,
-                                                                  I->skin_p54, I->skin_p94, rec, I->skin_pnt_out);
+                                                                  I->skin_p54, I->skin_p94, rec, I->skin_pnt_out, keys);
         CUDA_OK(cudaGetLastError());
         I->launches++;
         if (n > I->pts[1].points) I->pts[1].points = n;
@@ -1700,7 +1707,7 @@ size_t octree_cuc_skeleton_update(octree_glc_t* rc, const float* oldbones80, con
     I->skin_count = n;
     if (build_tree)
         nodes = build_from_device_paths(I, OCTREE_GLC_BUFFER_DYNAMIC_OCTREE, (const int*) I->skin_p14,
-                                        (const int*) I->skin_p54, (const int*) I->skin_p94, n, 0, maxlevel);
+                                        (const int*) I->skin_p54, (const int*) I->skin_p94, n, 0, maxlevel, keys);
     publish_memsize(rc, I);
     return nodes;
 }

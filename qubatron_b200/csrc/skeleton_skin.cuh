@@ -8,6 +8,7 @@
 // The outputs stay on the device: digits feed the tree build (octree_build.cuh), normals go straight into the
 // dynamic model's point records.
 #pragma once
+#include "octree_build.cuh"
 #include "octree_render.cuh"
 
 namespace qb
@@ -49,7 +50,8 @@ __device__ __forceinline__ float3 half3(float3 a)
 template <int DIV>
 __global__ void skin_kernel(const SkinParams S, size_t n, const float* __restrict__ positions,
                             const float* __restrict__ normals, int4* __restrict__ p14, int4* __restrict__ p54,
-                            int4* __restrict__ p94, float* __restrict__ rec, float* __restrict__ pnt_out)
+                            int4* __restrict__ p94, float* __restrict__ rec, float* __restrict__ pnt_out,
+                            unsigned long long* __restrict__ build_keys)
 {
     size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -161,6 +163,14 @@ __global__ void skin_kernel(const SkinParams S, size_t n, const float* __restric
     p14[i] = make_int4(d[0], d[1], d[2], d[3]);
     p54[i] = make_int4(d[4], d[5], d[6], d[7]);
     p94[i] = make_int4(d[8], d[9], d[10], d[11]);
+    if (build_keys) // the tree build's sort word (octree_build.cuh build_key_kernel), saving it a pass over the digits
+    {
+        unsigned long long k = 0;
+#pragma unroll
+        for (int level = 0; level < 12; level++)
+            if (level < S.maxlevel) k = (k << 3) | (unsigned long long) (d[level] & 7);
+        build_keys[i] = (k << BUILD_INDEX_BITS) | (unsigned long long) i;
+    }
 }
 
 } // namespace qb
