@@ -166,6 +166,7 @@ __global__ void build_emit_kernel(const int* __restrict__ tmp_child, const unsig
 {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total) return;
+    // `child` / `model` point at reference node 0 (= device node 1); child words hold DEVICE indices (octree_types.cuh)
     const int f = final_of_tmp[t];
     int       c[8];
     unsigned  m = 0;
@@ -173,7 +174,7 @@ __global__ void build_emit_kernel(const int* __restrict__ tmp_child, const unsig
     for (int s = 0; s < 8; s++)
     {
         const int k = tmp_child[(size_t) t * 8 + s];
-        c[s]        = k ? final_of_tmp[k] : 0;
+        c[s]        = k ? final_of_tmp[k] + 1 : 0;
         m |= (k ? 1u : 0u) << s;
     }
     child[2 * (size_t) f] = make_int4(c[0] | (int) ((m & 15u) << CHILD_MASK_SHIFT), c[1] | (int) ((m >> 4) << CHILD_MASK_SHIFT),
@@ -188,16 +189,17 @@ __global__ void export_nodes_kernel(const int4* __restrict__ child, const int* _
 {
     size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
     if (i >= nodes) return;
+    // `child` / `model` point at reference node 0 (= device node 1); child words are device indices
     const int4 lo = child[2 * i], hi = child[2 * i + 1];
     int*       o  = out12 + i * 12;
-    o[0]          = lo.x & (int) CHILD_INDEX_MASK;
-    o[1]          = lo.y & (int) CHILD_INDEX_MASK;
-    o[2]          = lo.z;
-    o[3]          = lo.w;
-    o[4]          = hi.x;
-    o[5]          = hi.y;
-    o[6]          = hi.z;
-    o[7]          = hi.w;
+    o[0]          = ref_node(lo.x & (int) CHILD_INDEX_MASK);
+    o[1]          = ref_node(lo.y & (int) CHILD_INDEX_MASK);
+    o[2]          = ref_node(lo.z);
+    o[3]          = ref_node(lo.w);
+    o[4]          = ref_node(hi.x);
+    o[5]          = ref_node(hi.y);
+    o[6]          = ref_node(hi.z);
+    o[7]          = ref_node(hi.w);
     o[8]          = model[i];
     o[9] = o[10] = o[11] = 0;
 }

@@ -51,15 +51,15 @@ using namespace qb;
 // octree_types.cuh.  Both kernels move 4-byte words.
 // ---------------------------------------------------------------------------
 
-// one 32-bit word of the reference node array -> traversal layout.  Child words
-// keep the index in bits 0-27; the node's child-exists mask lives in the top
-// nibble of words 0 and 1 (octree_types.cuh).  Atomics on disjoint bit fields make
-// concurrent updates of one node by several threads safe.
+// one 32-bit word of the reference node array -> traversal layout.  `child` / `model` point at reference node 0,
+// which is device node 1 (octree_types.cuh); child words keep the DEVICE index (reference index + 1, 0 = absent) in
+// bits 0-27; the node's child-exists mask lives in the top nibble of words 0 and 1.  Atomics on disjoint bit fields
+// make concurrent updates of one node by several threads safe.
 __device__ __forceinline__ void put_node_word(int* child, int* model, size_t node, int slot, int v)
 {
     if (slot < 8)
     {
-        const unsigned idx  = v > 0 ? ((unsigned) v & CHILD_INDEX_MASK) : 0u;
+        const unsigned idx  = v > 0 ? (((unsigned) v + 1u) & CHILD_INDEX_MASK) : 0u;
         unsigned*      w    = (unsigned*) child + node * 8 + slot;
         unsigned*      mw   = (unsigned*) child + node * 8 + (slot >> 2);
         const unsigned bit  = 1u << (CHILD_MASK_SHIFT + (slot & 3));
@@ -99,7 +99,7 @@ __global__ void relayout_octree_nodes_kernel(const int4* __restrict__ src, size_
     int4 a = src[3 * i], b = src[3 * i + 1], c = src[3 * i + 2];
     unsigned m = (a.x > 0 ? 1u : 0u) | (a.y > 0 ? 2u : 0u) | (a.z > 0 ? 4u : 0u) | (a.w > 0 ? 8u : 0u) |
                  (b.x > 0 ? 16u : 0u) | (b.y > 0 ? 32u : 0u) | (b.z > 0 ? 64u : 0u) | (b.w > 0 ? 128u : 0u);
-    auto ix = [](int v) { return v > 0 ? (int) ((unsigned) v & CHILD_INDEX_MASK) : 0; };
+    auto ix = [](int v) { return v > 0 ? (int) (((unsigned) v + 1u) & CHILD_INDEX_MASK) : 0; }; // device index
     int4 lo = make_int4(ix(a.x) | (int) ((m & 15u) << CHILD_MASK_SHIFT), ix(a.y) | (int) ((m >> 4) << CHILD_MASK_SHIFT),
                         ix(a.z), ix(a.w));
     int4 hi = make_int4(ix(b.x), ix(b.y), ix(b.z), ix(b.w));
@@ -189,10 +189,14 @@ struct DevArray
 
 struct Tree
 {
-    DevArray child; // 32 B per node
-    DevArray model; // 4 B per node
-    size_t   cap_nodes = 0;
-    size_t   nodes     = 0; // highest node uploaded + 1
+    DevArray child; // 32 B per device node: [0] the all-zero dummy, [n + 1] reference node n, one spare zero slot
+    DevArray model; // 4 B per device node
+    size_t   cap_nodes = 0;        // reference nodes the arrays hold (device nodes: cap_nodes + 2)
+    size_t   nodes     = 0;        // highest reference node uploaded + 1
+    size_t   sealed    = (size_t) -1; // extent whose clamp slot (device node nodes + 1) has been zeroed
+    // where the upload / build / export kernels see reference node 0
+    int* up_child() const { return (int*) child.ptr + 8; }
+    int* up_model() const { return (int*) model.ptr + 1; }
 };
 struct Points
 {
@@ -345,8 +349,8 @@ ScatterTargets scatter_targets(Impl* I)
     ScatterTargets T;
     for (int t = 0; t < 2; t++)
     {
-        T.child[t] = (int*) I->tree[t].child.ptr;
-        T.model[t] = (int*) I->tree[t].model.ptr;
+        T.child[t] = I->tree[t].up_child();
+        T.model[t] = I->tree[t].up_model();
         T.rec[t]   = (float*) I->pts[t].rec.ptr;
     }
     return T;
@@ -392,13 +396,14 @@ bool ensure_capacity(Impl* I, int buftype, size_t size)
     {
         Tree&  T     = I->tree[t];
         size_t nodes = (size + 47) / 48;
-        if (nodes > (size_t) CHILD_INDEX_MASK + 1) die("octree arrays are limited to 2^28 nodes per tree");
-        if (nodes <= T.cap_nodes) return false;
+        if (nodes > (size_t) CHILD_INDEX_MASK - 1) die("octree arrays are limited to 2^28 - 2 nodes per tree");
+        if (nodes <= T.cap_nodes && T.child.ptr) return false;
         flush_pending(I);
         size_t cap = grown(nodes);
-        dev_grow(I, T.child, cap * 32);
-        dev_grow(I, T.model, cap * 4);
+        dev_grow(I, T.child, (cap + 2) * 32); // + the dummy in front and the clamp slot behind
+        dev_grow(I, T.model, (cap + 2) * 4);
         T.cap_nodes = cap;
+        T.sealed    = (size_t) -1;
         return true;
     }
     Points& Pn     = I->pts[t];
@@ -441,12 +446,11 @@ void upload_bulk(Impl* I, const char* data, int buftype, size_t s, size_t e)
         {
             size_t nn = n / 48;
             relayout_octree_nodes_kernel<<<(unsigned) ((nn + 255) / 256), 256, 0, I->stream>>>(
-                (const int4*) I->stage_dev, off / 48, nn, (int4*) I->tree[t].child.ptr, (int*) I->tree[t].model.ptr);
+                (const int4*) I->stage_dev, off / 48, nn, (int4*) I->tree[t].up_child(), I->tree[t].up_model());
         }
         else if (is_octree(buftype))
             relayout_octree_kernel<<<blocks, 256, 0, I->stream>>>((const int*) I->stage_dev, off / 4, words,
-                                                                  (int*) I->tree[t].child.ptr,
-                                                                  (int*) I->tree[t].model.ptr);
+                                                                  I->tree[t].up_child(), I->tree[t].up_model());
         else
         {
             int which = (buftype == OCTREE_GLC_BUFFER_STATIC_NORMAL || buftype == OCTREE_GLC_BUFFER_DYNAMIC_NORMAL);
@@ -495,6 +499,25 @@ void upload_batched(Impl* I, const char* data, int buftype, size_t s, size_t e)
     I->batch_used += bytes;
     I->intervals[buftype][s] = std::make_pair((unsigned long long) e, (int) I->descs.size());
     I->descs.push_back(d);
+}
+
+// The kernels clamp every node index to device node `nodes + 1`, which must read as an empty node.  Memory behind
+// the extent is zero from allocation unless an earlier, larger extent left nodes there (octree_reset + rebuild):
+// zero that one slot whenever the extent has changed since the last launch.
+TreeDev tree_dev(Impl* I, int t)
+{
+    Tree& T = I->tree[t];
+    if (T.sealed != T.nodes)
+    {
+        CUDA_OK(cudaMemsetAsync((char*) T.child.ptr + (T.nodes + 1) * 32, 0, 32, I->stream));
+        CUDA_OK(cudaMemsetAsync((char*) T.model.ptr + (T.nodes + 1) * 4, 0, 4, I->stream));
+        T.sealed = T.nodes;
+    }
+    TreeDev D;
+    D.child = (const int4*) T.child.ptr;
+    D.model = (const int*) T.model.ptr;
+    D.nodes = (int) T.nodes + 1;
+    return D;
 }
 
 // smallest float d with acosf(d) < 0.02f: the host-libm form of the light-disc
@@ -661,7 +684,7 @@ void launch_fast_dyn(Impl* I, const FrameParams& P, unsigned blocks)
 void launch_fast(Impl* I, const FrameParams& P, unsigned blocks)
 {
     // a dynamic tree that is only a root (octree_reset, octree.c L89-93) has no geometry
-    const bool dyn = P.tree_d.nodes > 1;
+    const bool dyn = P.tree_d.nodes > 2; // .nodes counts the dummy in front
     if (I->div_mode == DIV_GLSL)
         dyn ? launch_fast_dyn<DIV_GLSL, true>(I, P, blocks) : launch_fast_dyn<DIV_GLSL, false>(I, P, blocks);
     else
@@ -747,10 +770,7 @@ void render_views(octree_glc_t* rc, int n, float width, float height, const floa
     memset(&P, 0, sizeof(P));
     for (int t = 0; t < 2; t++)
     {
-        TreeDev& T = t ? P.tree_d : P.tree_s;
-        T.child    = (const int4*) I->tree[t].child.ptr;
-        T.model    = (const int*) I->tree[t].model.ptr;
-        T.nodes    = (int) I->tree[t].nodes;
+        (t ? P.tree_d : P.tree_s) = tree_dev(I, t);
         PointsDev& Q = t ? P.pts_d : P.pts_s;
         Q.rec        = (const float4*) I->pts[t].rec.ptr;
         Q.points     = (int) I->pts[t].points;
@@ -1308,14 +1328,7 @@ T* scratch(Impl* I, size_t count)
 }
 void            scratch_free(Impl* I, void* p) { CUDA_OK(cudaFreeAsync(p, I->stream)); }
 inline unsigned nblk(size_t n) { return (unsigned) ((n + 255) / 256); }
-} // namespace
 
-extern "C" {
-
-} // extern "C"
-
-namespace
-{
 // paths on the device -> tree `t` in the traversal layout; returns the node count
 // keys_ready: optional scratch buffer of n sort words already filled by the producer (skin kernel); taken over
 size_t build_from_device_paths(Impl* I, int buftype, const int* p14, const int* p54, const int* p94, size_t n,
@@ -1435,7 +1448,7 @@ size_t build_from_device_paths(Impl* I, int buftype, const int* p14, const int* 
     CUDA_OK(cudaStreamSynchronize(st));
     ensure_capacity(I, buftype, (size_t) total * 48);
     build_emit_kernel<<<nblk(total), 256, 0, st>>>(tmp_child, tmp_key, final_of_tmp, total, first_modind,
-                                                   (int4*) I->tree[t].child.ptr, (int*) I->tree[t].model.ptr);
+                                                   (int4*) I->tree[t].up_child(), I->tree[t].up_model());
     CUDA_OK(cudaGetLastError());
     launches += 1;
     I->tree[t].nodes = (size_t) total; // like octree_reset + rebuild: the old extent is gone
@@ -1783,11 +1796,9 @@ void octree_cuc_particles_update(octree_glc_t* rc, int kind, int count, int maxl
     cudaStream_t st = I->stream;
     FrameParams  P;
     memset(&P, 0, sizeof(P));
-    P.tree_s.child = (const int4*) I->tree[0].child.ptr; // particle_glc.c L106-107: the static octree only
-    P.tree_s.model = (const int*) I->tree[0].model.ptr;
-    P.tree_s.nodes = (int) I->tree[0].nodes;
+    P.tree_s       = tree_dev(I, 0); // particle_glc.c L106-107: the static octree only
     P.tree_d       = P.tree_s;
-    P.tree_d.nodes = 0;
+    P.tree_d.nodes = 0; // every index clamps to the dummy
     P.basecube[0]  = 0.0f;
     P.basecube[1] = P.basecube[2] = P.basecube[3] = basesize;
     P.maxlevel                                    = maxlevel;
@@ -1841,12 +1852,9 @@ void octree_cuc_trace_lines(octree_glc_t* rc, size_t n, const float* pos, const 
     FrameParams  P;
     memset(&P, 0, sizeof(P));
     const int t     = dynamic_tree ? 1 : 0;
-    P.tree_s.child  = (const int4*) I->tree[t].child.ptr; // the queried tree in the first slot, nothing in the second
-    P.tree_s.model  = (const int*) I->tree[t].model.ptr;
-    P.tree_s.nodes  = (int) I->tree[t].nodes;
-    P.tree_d.child  = (const int4*) I->tree[t].child.ptr;
-    P.tree_d.model  = (const int*) I->tree[t].model.ptr;
-    P.tree_d.nodes  = 0;
+    P.tree_s        = tree_dev(I, t); // the queried tree in the first slot, nothing in the second
+    P.tree_d        = P.tree_s;
+    P.tree_d.nodes  = 0; // every index clamps to the dummy
     P.basecube[0]   = 0.0f;
     P.basecube[1] = P.basecube[2] = P.basecube[3] = basesize;
     P.maxlevel                                    = maxlevel;
@@ -1898,8 +1906,8 @@ size_t octree_cuc_download_octree(octree_glc_t* rc, octree_glc_buffer_t buftype,
     const size_t n = I->tree[t].nodes;
     if (nodes12_host == nullptr || capacity_nodes < n) return n;
     int* out = scratch<int>(I, n * 12);
-    export_nodes_kernel<<<nblk(n), 256, 0, I->stream>>>((const int4*) I->tree[t].child.ptr,
-                                                        (const int*) I->tree[t].model.ptr, n, out);
+    export_nodes_kernel<<<nblk(n), 256, 0, I->stream>>>((const int4*) I->tree[t].up_child(), I->tree[t].up_model(), n,
+                                                        out);
     CUDA_OK(cudaGetLastError());
     I->launches++;
     CUDA_OK(cudaMemcpyAsync(nodes12_host, out, n * 48, cudaMemcpyDeviceToHost, I->stream));

@@ -163,24 +163,20 @@ __device__ __forceinline__ bool in_x(const Cube& c, float x) { return c.x0 < x &
 __device__ __forceinline__ bool in_y(const Cube& c, float y) { return c.y1 > y && y >= c.y0; }
 __device__ __forceinline__ bool in_z(const Cube& c, float z) { return c.z1 > z && z >= c.z0; }
 
-// the 8 child indices of a node.  Node 0 below the root level means "this tree
-// has nothing here" (octree_fsh.c L129); nodes past the uploaded range read 0.
+// the 8 child indices (device indices, octree_types.cuh) of a node.  Device node 0 is the empty dummy that "this
+// tree has nothing here" (octree_fsh.c L129) leads to; nodes past the uploaded range read 0.
 struct Children
 {
     int4 lo, hi;
 };
-__device__ __forceinline__ Children load_children(const TreeDev& t, int node, int level)
+__device__ __forceinline__ Children load_children(const TreeDev& t, int node, int /*level*/)
 {
     Children c;
-    c.lo = make_int4(0, 0, 0, 0);
-    c.hi = make_int4(0, 0, 0, 0);
-    if ((node != 0 || level == 0) && (unsigned) node < (unsigned) t.nodes)
-    {
-        c.lo = __ldg(t.child + 2 * (size_t) node);
-        c.hi = __ldg(t.child + 2 * (size_t) node + 1);
-        c.lo.x &= (int) CHILD_INDEX_MASK; // words 0/1 carry the child-exists mask in their top nibble
-        c.lo.y &= (int) CHILD_INDEX_MASK;
-    }
+    node = tree_clamp(t, node);
+    c.lo = __ldg(t.child + 2 * (size_t) node);
+    c.hi = __ldg(t.child + 2 * (size_t) node + 1);
+    c.lo.x &= (int) CHILD_INDEX_MASK; // words 0/1 carry the child-exists mask in their top nibble
+    c.lo.y &= (int) CHILD_INDEX_MASK;
     return c;
 }
 __device__ __forceinline__ int child_of(const Children& c, int oct)
@@ -193,10 +189,9 @@ __device__ __forceinline__ int child_of(const Children& c, int oct)
     int h = (oct & 2) ? f : e;
     return (oct & 4) ? h : l;
 }
-__device__ __forceinline__ int model_of(const TreeDev& t, int node, int level)
+__device__ __forceinline__ int model_of(const TreeDev& t, int node, int /*level*/)
 {
-    if ((node != 0 || level == 0) && (unsigned) node < (unsigned) t.nodes) return __ldg(t.model + node);
-    return 0;
+    return __ldg(t.model + tree_clamp(t, node));
 }
 
 // base-cube entry (octree_fsh.c L157-211).  Returns false on `discard`.
@@ -311,8 +306,8 @@ __device__ __noinline__ TraceResult trace_generic(const FrameParams& P, float3 p
     GenericLevel stck[GENERIC_STACK];
     int          level = 0;
     stck[0].cube       = make_float4(P.basecube[0], P.basecube[1], P.basecube[2], P.basecube[3]);
-    stck[0].socti      = 0;
-    stck[0].docti      = 0;
+    stck[0].socti      = ROOT_NODE;
+    stck[0].docti      = TWIN == TRACE_PARTICLE ? 0 : ROOT_NODE;
     stck[0].ispsi      = 0;
     stck[0].octs       = 0;
     stck[0].isps[0]    = entry;
@@ -332,14 +327,14 @@ __device__ __noinline__ TraceResult trace_generic(const FrameParams& P, float3 p
             res.iw      = isp.w;
             res.status  = 1;
             res.tx = tlf.x, res.ty = tlf.y, res.tz = tlf.z, res.tw = tlf.w;
-            res.node_s  = stck[level].socti;
-            res.node_d  = stck[level].docti;
-            res.model_s = model_of(P.tree_s, res.node_s, level);
-            res.model_d = model_of(P.tree_d, res.node_d, level);
+            res.node_s  = ref_node(stck[level].socti);
+            res.node_d  = ref_node(stck[level].docti);
+            res.model_s = model_of(P.tree_s, stck[level].socti, level);
+            res.model_d = model_of(P.tree_d, stck[level].docti, level);
             if (COUNT)
             {
-                if (level == 0 || res.node_s != 0) cnt.v[CNT_LEAF_S]++;
-                if (level == 0 || res.node_d != 0) cnt.v[CNT_LEAF_D]++;
+                if (stck[level].socti != 0) cnt.v[CNT_LEAF_S]++;
+                if (stck[level].docti != 0) cnt.v[CNT_LEAF_D]++;
             }
             return res;
         }
@@ -357,15 +352,15 @@ __device__ __noinline__ TraceResult trace_generic(const FrameParams& P, float3 p
             // particle_vsh.c L108-119 addresses texel (3i mod 8192) + octi/4 of row 3i / 8192 WITHOUT wrapping into the
             // next row (octree_fsh.c L130-135 wraps): for a node whose first texel is the last of its row, children
             // 4..7 are fetched outside the texture and read 0
-            if (TWIN == TRACE_PARTICLE && ((3 * sn) & 8191) == 8191) cs.hi = make_int4(0, 0, 0, 0);
+            if (TWIN == TRACE_PARTICLE && sn > 0 && ((3 * (sn - 1)) & 8191) == 8191) cs.hi = make_int4(0, 0, 0, 0);
         }
 
         if (stck[level].ispsi == 0) // L251-330
         {
             if (COUNT)
             {
-                if (level == 0 || sn != 0) cnt.v[CNT_EXPAND_S]++;
-                if (level == 0 || dn != 0) cnt.v[CNT_EXPAND_D]++;
+                if (sn != 0) cnt.v[CNT_EXPAND_S]++;
+                if (dn != 0) cnt.v[CNT_EXPAND_D]++;
             }
             Cube c;
             c.x0 = tlf.x;

@@ -23,12 +23,25 @@
 namespace qb
 {
 
+// Node n of the reference array lives at DEVICE index n + 1 and child words hold device indices, so that 0 -- the
+// reference's "no child" -- addresses device node 0, an all-zero dummy (no children, model 0).  Descending into an
+// absent subtree therefore needs no test: it reads the dummy and stays there (octree_fsh.c L129 returns 0 for
+// "node 0 below the root level").  The root is device node 1.  Never-uploaded nodes are zero as well, i.e. empty.
+// `nodes` = device index of a slot that is kept zero just past the uploaded extent: an index beyond the extent is
+// clamped to it with one min, which keeps "reads beyond the uploaded range return 0" without a compare-and-branch.
 struct TreeDev
 {
-    const int4* child; // 2 x int4 per node
-    const int*  model; // oct[8] per node
-    int         nodes; // nodes uploaded so far (reads beyond return 0)
+    const int4* child; // 2 x int4 per device node
+    const int*  model; // oct[8] per device node
+    int         nodes; // reference nodes uploaded so far + 1 = the zero slot every larger index is clamped to
 };
+__device__ __forceinline__ int tree_clamp(const TreeDev& t, int node)
+{
+    return (int) min((unsigned) node, (unsigned) t.nodes);
+}
+// device index -> reference index for reporting (0 for "absent", like the reference's stack)
+__device__ __forceinline__ int ref_node(int dev) { return dev > 0 ? dev - 1 : 0; }
+constexpr int ROOT_NODE = 1;
 
 struct PointsDev
 {
