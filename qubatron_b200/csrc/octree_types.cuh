@@ -1,10 +1,12 @@
 // octree_types.cuh -- device-side data layout and per-frame parameter block.
 //
 // HBM layout (see DESIGN.md "Data layout"):
-//   child_{s,d} : int4[2*nodes]  -- the 8 child indices of a node, 32 B, one
+//   child_{s,d} : int4[2*(nodes+2)] -- device node 0 = all-zero dummy, reference node n
+//                                   at device node n + 1 (see TreeDev below);
+//                                   the 8 child indices of a node, 32 B, one
 //                                   aligned sector per node expansion
 //                                   (reference node = int32[12], octree.c L11-14).
-//                                   Bits 0-27 of a word = child node index
+//                                   Bits 0-27 of a word = child DEVICE index
 //                                   (0 = absent); the top 4 bits of words 0 and 1
 //                                   hold the node's 8-bit "child exists" mask
 //                                   (bit k of the mask = child k > 0), maintained by
