@@ -343,6 +343,9 @@ def bench_config(meta, args, world):
                            meta["dynamic_nodes"], MAXLEVEL, BASESIZE, WIDTH, HEIGHT, len(meta["cameras"])),
             "scale": args.scale, "width": WIDTH, "height": HEIGHT, "maxlevel": MAXLEVEL,
             "parallelism": "image tiles %dx%d interleaved over %d GPU(s), octree replicated" % (args.tile, args.tile, world),
+            "tile_order": "heaviest first, from the tile costs measured the last time the same view was rendered "
+                          "(each of the cycled poses is first seen in warm-up); the ordering kernel runs inside the "
+                          "timed step; QB_TILE_FEEDBACK=0 renders tiles in image order",
             "l2": "flushed before every step (256 MiB memset, outside the step's event pair); scene arrays "
                   "(%.1f GB) also exceed L2" % ((meta["static_nodes"] + meta["dynamic_nodes"]) * 36e-9
                                                 + (meta["static_points"] + meta["dynamic_points"]) * 32e-9)}

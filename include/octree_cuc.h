@@ -261,6 +261,12 @@ size_t octree_cuc_skeleton_update(octree_glc_t* rc, const float* oldbones80, con
 size_t octree_cuc_skeleton_read_out(octree_glc_t* rc, int32_t* oct14, int32_t* oct54, int32_t* oct94, float* nrm_out,
                                     float* pnt_out);
 
+/* Tile scheduling by measured cost (fast kernel, single-view frames; on by default).  The kernel records how many
+ * warp-cycles every 64 x 64 tile took; the next frame of the same view -- or, for a view not seen before, of the most
+ * recent one -- launches its tiles heaviest first, so that the longest rays of a frame do not end up running alone
+ * at the end of the launch.  Pixels are independent: the frame is bit-identical either way. */
+void octree_cuc_set_tile_feedback(octree_glc_t* rc, int on);
+
 /* "Next" row (second half): the presentation pass of octree_glc_update (octree_glc.c L308-351).  With
  * present enabled every single-view, unsharded octree_glc_update also produces what the reference leaves in the
  * window's back buffer: the frame drawn LINEAR-filtered into (int)width x (int)height pixels (all four channels),

@@ -90,6 +90,7 @@ _PROTOS = {
                                                 C.c_float, C.c_int]),
     "octree_cuc_skeleton_read_out": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_void_p, C.c_void_p, C.c_void_p,
                                                   C.c_void_p, C.c_void_p]),
+    "octree_cuc_set_tile_feedback": (None, [C.POINTER(octree_glc_t), C.c_int]),
     "octree_cuc_enable_present": (None, [C.POINTER(octree_glc_t), C.c_int]),
     "octree_cuc_read_window": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_void_p, C.c_size_t, C.POINTER(C.c_int),
                                             C.POINTER(C.c_int)]),
@@ -351,6 +352,9 @@ class OctreeGlc:
                                               p94.ctypes.data_as(C.c_void_p), nrm.ctypes.data_as(C.c_void_p),
                                               pnt.ctypes.data_as(C.c_void_p))
         return np.concatenate([p14, p54, p94], axis=1), nrm, pnt
+
+    def set_tile_feedback(self, on=True):
+        self.lib.octree_cuc_set_tile_feedback(self._p, int(bool(on)))
 
     def enable_present(self, on=True):
         self.lib.octree_cuc_enable_present(self._p, int(bool(on)))

@@ -276,6 +276,23 @@ struct Impl
     int4 * skin_p14 = nullptr, *skin_p54 = nullptr, *skin_p94 = nullptr;
     float* skin_pnt_out = nullptr;
     size_t skin_count   = 0; // points of the last update
+    // tile scheduling by measured cost (fast kernel): per remembered view an order of this rank's tiles
+    static constexpr int ORDER_SLOTS = 8;
+    struct ViewKey
+    {
+        float pos[3], ang[3], width, height, lighta;
+        int   quality, maxlevel, tiles;
+    };
+    bool      feedback_on  = true;
+    int*      order_dev    = nullptr; // [ORDER_SLOTS][order_cap]
+    unsigned* cost_dev[2]  = {nullptr, nullptr};
+    int       order_cap    = 0;
+    int       cost_phase   = 0;
+    ViewKey   order_key[ORDER_SLOTS];
+    uint64_t  order_used[ORDER_SLOTS] = {0};
+    bool      order_valid[ORDER_SLOTS] = {false};
+    int       order_last   = -1;
+    uint64_t  order_clock  = 0;
     // presentation ("next" row 8f #4b): the window image of the last frame
     bool    present_on  = false;
     uchar4* window      = nullptr;
@@ -843,19 +860,93 @@ void render_views(octree_glc_t* rc, int n, float width, float height, const floa
 
     const unsigned blocks = (unsigned) ((size_t) P.tiles_mine * P.blocks_per_tile_x * P.blocks_per_tile_y * n);
     CUDA_OK(cudaEventRecord(I->ev0, I->stream));
+    bool ev1_recorded = false;
     if (blocks)
     {
         bool fast = I->kernel_choice == 2 || (I->kernel_choice == 0 && grid_is_exact(basesize, maxlevel));
         if (fast && !grid_is_exact(basesize, maxlevel)) die("fast kernel requested for a base cube that is not exact");
+        int order_slot = -1;
+        if (fast && n == 1 && I->feedback_on && P.tiles_mine > 1)
+        {
+            // the order learned for this exact view if it has been rendered before, else a copy of the most recent one
+            const int nt = P.tiles_mine;
+            if (nt > I->order_cap)
+            {
+                CUDA_OK(cudaStreamSynchronize(I->stream));
+                if (I->order_dev) CUDA_OK(cudaFree(I->order_dev));
+                for (int k = 0; k < 2; k++)
+                    if (I->cost_dev[k]) CUDA_OK(cudaFree(I->cost_dev[k]));
+                I->order_cap = nt + nt / 4 + 64;
+                CUDA_OK(cudaMalloc(&I->order_dev, sizeof(int) * Impl::ORDER_SLOTS * I->order_cap));
+                for (int k = 0; k < 2; k++)
+                {
+                    CUDA_OK(cudaMalloc(&I->cost_dev[k], sizeof(unsigned) * I->order_cap));
+                    CUDA_OK(cudaMemsetAsync(I->cost_dev[k], 0, sizeof(unsigned) * I->order_cap, I->stream));
+                }
+                for (int k = 0; k < Impl::ORDER_SLOTS; k++) I->order_valid[k] = false;
+                I->order_last = -1;
+            }
+            Impl::ViewKey key;
+            memset(&key, 0, sizeof(key));
+            memcpy(key.pos, positions, 12);
+            memcpy(key.ang, angles, 12);
+            key.width = width, key.height = height, key.lighta = lighta;
+            key.quality = quality, key.maxlevel = maxlevel, key.tiles = nt;
+            int lru = -1; // a free slot if there is one, else the least recently used
+            for (int k = 0; k < Impl::ORDER_SLOTS; k++)
+            {
+                if (I->order_valid[k] && memcmp(&I->order_key[k], &key, sizeof(key)) == 0) order_slot = k;
+                if (lru < 0)
+                    lru = k;
+                else if (I->order_valid[lru] && (!I->order_valid[k] || I->order_used[k] < I->order_used[lru]))
+                    lru = k;
+            }
+            if (I->order_last >= 0 && I->order_key[I->order_last].tiles != nt)
+            {
+                // another tiling: measurements of the old one mean nothing here
+                for (int k = 0; k < 2; k++)
+                    CUDA_OK(cudaMemsetAsync(I->cost_dev[k], 0, sizeof(unsigned) * I->order_cap, I->stream));
+            }
+            if (order_slot < 0)
+            {
+                order_slot   = lru;
+                int* dst     = I->order_dev + (size_t) order_slot * I->order_cap;
+                const int ls = I->order_last;
+                if (ls >= 0 && I->order_valid[ls] && I->order_key[ls].tiles == nt && ls != order_slot)
+                    CUDA_OK(cudaMemcpyAsync(dst, I->order_dev + (size_t) ls * I->order_cap, sizeof(int) * nt,
+                                            cudaMemcpyDeviceToDevice, I->stream));
+                else if (!(ls == order_slot && I->order_valid[ls] && I->order_key[ls].tiles == nt))
+                    tile_identity_kernel<<<(nt + 255) / 256, 256, 0, I->stream>>>(dst, nt);
+                I->order_key[order_slot]   = key;
+                I->order_valid[order_slot] = true;
+            }
+            I->order_used[order_slot] = ++I->order_clock;
+            I->order_last             = order_slot;
+            P.tile_order              = I->order_dev + (size_t) order_slot * I->order_cap;
+            P.tile_cost               = I->cost_dev[I->cost_phase];
+        }
         if (fast)
+        {
             launch_fast(I, P, blocks);
+            if (order_slot >= 0)
+            {
+                // after the frame: this view's next order from the costs just measured (not part of ev0..ev1)
+                CUDA_OK(cudaEventRecord(I->ev1, I->stream));
+                ev1_recorded = true;
+                tile_rank_kernel<<<(P.tiles_mine + 127) / 128, 128, 0, I->stream>>>(
+                    I->cost_dev[I->cost_phase], P.tiles_mine, I->order_dev + (size_t) order_slot * I->order_cap,
+                    I->cost_dev[I->cost_phase ^ 1]);
+                I->cost_phase ^= 1;
+                I->launches++;
+            }
+        }
         else
             launch_generic(I, P, blocks);
         CUDA_OK(cudaGetLastError());
         I->launches++;
         I->last_kernel = fast ? 2 : 1;
     }
-    CUDA_OK(cudaEventRecord(I->ev1, I->stream));
+    if (!ev1_recorded) CUDA_OK(cudaEventRecord(I->ev1, I->stream));
     if (I->present_on && n == 1 && I->shard_world == 1) // octree_glc.c L308-351; after ev1: not part of the frame time
     {
         const int ww = (int) width, wh = (int) height;
@@ -938,6 +1029,7 @@ octree_glc_t octree_glc_init(char* path)
     }
     CUDA_OK(cudaStreamCreateWithFlags(&I->own_stream, cudaStreamNonBlocking));
     I->stream = I->own_stream;
+    if (getenv("QB_TILE_FEEDBACK")) I->feedback_on = atoi(getenv("QB_TILE_FEEDBACK")) != 0; // for A/B runs
     CUDA_OK(cudaEventCreate(&I->ev0));
     CUDA_OK(cudaEventCreate(&I->ev1));
     for (int i = 0; i < VIEW_RING; i++) CUDA_OK(cudaEventCreateWithFlags(&I->slot_ev[i], cudaEventDisableTiming));
@@ -981,6 +1073,9 @@ void octree_cuc_destroy(octree_glc_t* rc)
     if (I->frame) cudaFree(I->frame);
     if (I->frame_alt) cudaFree(I->frame_alt);
     if (I->window) cudaFree(I->window);
+    if (I->order_dev) cudaFree(I->order_dev);
+    for (int k = 0; k < 2; k++)
+        if (I->cost_dev[k]) cudaFree(I->cost_dev[k]);
     for (void* p : {(void*) I->skin_pos, (void*) I->skin_nrm, (void*) I->skin_p14, (void*) I->skin_p54,
                     (void*) I->skin_p94, (void*) I->skin_pnt_out, (void*) I->part_finished})
         if (p) cudaFree(p);
@@ -1094,6 +1189,8 @@ size_t octree_cuc_read_frame(octree_glc_t* rc, uint8_t* rgba_host, size_t capaci
 }
 
 void octree_cuc_enable_present(octree_glc_t* rc, int on) { impl_of(rc)->present_on = on != 0; }
+
+void octree_cuc_set_tile_feedback(octree_glc_t* rc, int on) { impl_of(rc)->feedback_on = on != 0; }
 
 size_t octree_cuc_read_window(octree_glc_t* rc, uint8_t* rgba_host, size_t capacity, int* width, int* height)
 {

@@ -80,6 +80,28 @@ __global__ void trace_lines_kernel(const FrameParams P, size_t n, const float* _
     }
 }
 
+// order[r] = the tile with the r-th largest cost (ties in tile order); clears the cost array of the next frame
+__global__ void tile_rank_kernel(const unsigned* __restrict__ cost, int n, int* __restrict__ order,
+                                 unsigned* __restrict__ next_cost)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned c = cost[i];
+    int            r = 0;
+    for (int j = 0; j < n; j++)
+    {
+        const unsigned cj = __ldg(cost + j);
+        r += (cj > c || (cj == c && j < i)) ? 1 : 0;
+    }
+    order[r]     = i;
+    next_cost[i] = 0;
+}
+__global__ void tile_identity_kernel(int* __restrict__ order, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) order[i] = i;
+}
+
 // pixel of thread `tid` inside the CTA's 16x8 block: each warp covers an 8x4
 // patch (lanes row-major inside it) so the 32 rays of a warp stay coherent
 __device__ __forceinline__ void block_pixel(int tid, int& lx, int& ly)

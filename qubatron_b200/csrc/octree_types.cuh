@@ -108,6 +108,12 @@ struct FrameParams
     int blocks_per_tile_x, blocks_per_tile_y;
     int tiles_mine; // number of tiles this rank renders per view
 
+    // tile scheduling by measured cost (fast kernel, single view): launch position -> tile of this rank, heaviest
+    // first, learned from an earlier frame of the same or the most recent view; the kernel accumulates every
+    // tile's warp-cycles for the next frame.  Both null = tiles in image order.
+    const int* tile_order;
+    unsigned*  tile_cost;
+
     // views
     const ViewParams* views; // device array, n_views entries
     int               n_views;
