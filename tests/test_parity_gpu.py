@@ -685,6 +685,48 @@ def test_presentation_at_full_size_equals_the_oracle(scene_c1):
     rc.destroy()
 
 
+def test_tile_feedback_changes_the_order_not_the_frame(scene_c1):
+    """Tile scheduling by measured cost (octree_cuc_set_tile_feedback): whatever order the tiles are launched in --
+    image order, the order learned from the previous rendering of the view, an order inherited from another view,
+    another tiling after a resize, more remembered views than slots, a sharded frame -- every byte of the frame and
+    of the parity planes equals the frame rendered in image order."""
+    views = [S.CAMERA_C1, ((760.0, 125.0, 225.0), (2.0, 0.3, 0.0)), ((700.0, 180.0, 300.0), (0.9, -0.4, 0.0))]
+    views += [((700.0 + 3.0 * k, 150.0, 350.0), (0.4636, 0.0, 0.0)) for k in range(9)]   # > 8 remembered views
+    sizes = [(640, 360), (333, 207), (640, 360)]
+    want = {}
+    rc = K.OctreeGlc(b"", device=0)
+    rc.upload_scene(scene_c1)
+    rc.enable_aux(True)
+    rc.set_tile_feedback(False)
+    for (W, H) in set(sizes):
+        for i, (pos, ang) in enumerate(views):
+            rc.update(W, H, pos, ang)
+            want[(W, H, i)] = (rc.read_frame(), rc.read_aux())
+    rc.set_tile_feedback(True)
+    for rep in range(3):
+        for (W, H) in sizes:
+            for i, (pos, ang) in enumerate(views):
+                rc.update(W, H, pos, ang)
+                frame, (flags, aux) = rc.read_frame(), rc.read_aux()
+                ref_frame, (ref_flags, ref_aux) = want[(W, H, i)]
+                assert np.array_equal(frame, ref_frame), (rep, W, H, i)
+                assert np.array_equal(flags, ref_flags) and np.array_equal(aux, ref_aux), (rep, W, H, i)
+    # a shard of the frame: the untouched tiles keep the marker, the rendered ones equal the full frame
+    rc.set_shard(1, 3, 64, 64)
+    for rep in range(3):
+        rc.update(640, 360, *views[0])
+        got = rc.read_frame()
+        own = S_tile_mask(640, 360, 64, 1, 3)
+        assert np.array_equal(got[own], want[(640, 360, 0)][0][own]), rep
+    rc.destroy()
+
+
+def S_tile_mask(W, H, tile, rank, world):
+    ty, tx = np.meshgrid(np.arange(H) // tile, np.arange(W) // tile, indexing="ij")
+    tiles_x = (W + tile - 1) // tile
+    return ((ty * tiles_x + tx) % world) == rank
+
+
 def test_gpu_voxelise_and_bulk_build_equal_the_host_model():
     """octree_cuc_voxelise_and_build ("next" row 8f #3): the same survivors in the same order as the qmc rules
     (host voxeliser, itself byte-identical to the reference qmc binary in tests/test_host_model.py), the same
