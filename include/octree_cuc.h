@@ -116,6 +116,12 @@ size_t octree_cuc_read_frame(octree_glc_t* rc, uint8_t* rgba_host, size_t capaci
  * written (0 if the buffer is too small). */
 size_t octree_cuc_read_frame_async(octree_glc_t* rc, uint8_t* rgba_host, size_t capacity);
 void   octree_cuc_wait_reads(octree_glc_t* rc);
+/* The same overlap for a frame whose render target must stay where it is -- rank 0's framebuffer that the other
+ * ranks store their tiles into over NVLink (octree_cuc_ipc_export_frame): the finished frame is first copied device to
+ * device (8 MB: a few microseconds, on the render stream, i.e. after whatever fence the caller queued there) into one
+ * of two staging buffers, and goes to the page-locked host buffer from there on the copy stream while the next frame
+ * renders.  octree_cuc_wait_reads waits for these copies too. */
+size_t octree_cuc_read_frame_staged(octree_glc_t* rc, uint8_t* rgba_host, size_t capacity);
 
 /* device address of the RGBA8 frame (valid until the next resize) */
 uint64_t octree_cuc_frame_device(octree_glc_t* rc);

@@ -90,6 +90,7 @@ _PROTOS = {
                                                 C.c_float, C.c_int]),
     "octree_cuc_skeleton_read_out": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_void_p, C.c_void_p, C.c_void_p,
                                                   C.c_void_p, C.c_void_p]),
+    "octree_cuc_read_frame_staged": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_void_p, C.c_size_t]),
     "octree_cuc_set_tile_feedback": (None, [C.POINTER(octree_glc_t), C.c_int]),
     "octree_cuc_enable_present": (None, [C.POINTER(octree_glc_t), C.c_int]),
     "octree_cuc_read_window": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_void_p, C.c_size_t, C.POINTER(C.c_int),
@@ -219,6 +220,13 @@ class OctreeGlc:
         got = self.lib.octree_cuc_read_frame_async(self._p, out.ctypes.data_as(C.c_void_p), out.nbytes)
         if got == 0:
             raise RuntimeError("read_frame_async: no frame or buffer too small")
+        return out
+
+    def read_frame_staged(self, out):
+        """Like read_frame_async with the render target left in place (sharded frames); see wait_reads()."""
+        got = self.lib.octree_cuc_read_frame_staged(self._p, out.ctypes.data_as(C.c_void_p), out.nbytes)
+        if got == 0:
+            raise RuntimeError("read_frame_staged: no frame or buffer too small")
         return out
 
     def wait_reads(self):

@@ -246,6 +246,14 @@ struct Impl
     cudaEvent_t         ev_render[2] = {};
     cudaEvent_t         ev_copy[2]   = {};
     bool                copy_pending[2] = {};
+    // staged async readback (render target stays in place: frames other ranks store into over NVLink)
+    uchar4*     stage_frame[2]   = {nullptr, nullptr};
+    size_t      stage_cap        = 0; // pixels
+    cudaEvent_t ev_stage_ready[2] = {};
+    cudaEvent_t ev_stage_done[2]  = {};
+    bool        stage_pending[2]  = {};
+    bool        stage_on          = false;
+    int         stage_k           = 0;
     uint64_t            ext_target  = 0;
     size_t              ext_pitch   = 0;
     uint8_t*            flags       = nullptr;
@@ -1085,16 +1093,21 @@ void octree_cuc_destroy(octree_glc_t* rc)
             if (I->part_pos[k][b]) cudaFree(I->part_pos[k][b]);
             if (I->part_spd[k][b]) cudaFree(I->part_spd[k][b]);
         }
+    if (I->copy_stream) cudaStreamSynchronize(I->copy_stream);
     if (I->ring_on)
-    {
-        cudaStreamSynchronize(I->copy_stream);
         for (int i = 0; i < 2; i++)
         {
             cudaEventDestroy(I->ev_render[i]);
             cudaEventDestroy(I->ev_copy[i]);
         }
-        cudaStreamDestroy(I->copy_stream);
-    }
+    if (I->stage_on)
+        for (int i = 0; i < 2; i++)
+        {
+            cudaEventDestroy(I->ev_stage_ready[i]);
+            cudaEventDestroy(I->ev_stage_done[i]);
+            if (I->stage_frame[i]) cudaFree(I->stage_frame[i]);
+        }
+    if (I->copy_stream) cudaStreamDestroy(I->copy_stream);
     if (I->flags) cudaFree(I->flags);
     if (I->aux) cudaFree(I->aux);
     if (I->views_host) cudaFreeHost(I->views_host);
@@ -1222,7 +1235,7 @@ size_t octree_cuc_read_frame_async(octree_glc_t* rc, uint8_t* rgba_host, size_t 
     if (!I->ring_on)
     {
         // first use: from now on frames alternate between two buffers; the frame just rendered is in `frame`
-        CUDA_OK(cudaStreamCreateWithFlags(&I->copy_stream, cudaStreamNonBlocking));
+        if (!I->copy_stream) CUDA_OK(cudaStreamCreateWithFlags(&I->copy_stream, cudaStreamNonBlocking));
         for (int i = 0; i < 2; i++)
         {
             CUDA_OK(cudaEventCreateWithFlags(&I->ev_render[i], cudaEventDisableTiming));
@@ -1241,10 +1254,55 @@ size_t octree_cuc_read_frame_async(octree_glc_t* rc, uint8_t* rgba_host, size_t 
     return bytes;
 }
 
+size_t octree_cuc_read_frame_staged(octree_glc_t* rc, uint8_t* rgba_host, size_t capacity)
+{
+    Impl*        I      = impl_of(rc);
+    const size_t pixels = (size_t) I->W * I->H * (I->n_views ? I->n_views : 1);
+    const size_t bytes  = pixels * 4;
+    if (I->ext_target && I->ext_pitch && I->ext_pitch != (size_t) I->W) die("read_frame_staged: pitched external target");
+    if (bytes == 0 || capacity < bytes) return 0;
+    if (!I->stage_on)
+    {
+        if (!I->copy_stream) CUDA_OK(cudaStreamCreateWithFlags(&I->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++)
+        {
+            CUDA_OK(cudaEventCreateWithFlags(&I->ev_stage_ready[i], cudaEventDisableTiming));
+            CUDA_OK(cudaEventCreateWithFlags(&I->ev_stage_done[i], cudaEventDisableTiming));
+        }
+        I->stage_on = true;
+    }
+    if (pixels > I->stage_cap)
+    {
+        CUDA_OK(cudaStreamSynchronize(I->copy_stream));
+        CUDA_OK(cudaStreamSynchronize(I->stream));
+        for (int i = 0; i < 2; i++)
+        {
+            if (I->stage_frame[i]) CUDA_OK(cudaFree(I->stage_frame[i]));
+            CUDA_OK(cudaMalloc(&I->stage_frame[i], bytes));
+            I->stage_pending[i] = false;
+        }
+        I->memsize += 2 * (pixels - I->stage_cap) * 4;
+        I->stage_cap = pixels;
+        publish_memsize(rc, I);
+    }
+    const int   k   = I->stage_k;
+    I->stage_k ^= 1;
+    const void* src = (const void*) (uintptr_t) octree_cuc_frame_device(rc);
+    // the host copy that last read this staging buffer must be done before it is overwritten
+    if (I->stage_pending[k]) CUDA_OK(cudaStreamWaitEvent(I->stream, I->ev_stage_done[k], 0));
+    CUDA_OK(cudaMemcpyAsync(I->stage_frame[k], src, bytes, cudaMemcpyDeviceToDevice, I->stream));
+    CUDA_OK(cudaEventRecord(I->ev_stage_ready[k], I->stream));
+    CUDA_OK(cudaStreamWaitEvent(I->copy_stream, I->ev_stage_ready[k], 0));
+    CUDA_OK(cudaMemcpyAsync(rgba_host, I->stage_frame[k], bytes, cudaMemcpyDeviceToHost, I->copy_stream));
+    CUDA_OK(cudaEventRecord(I->ev_stage_done[k], I->copy_stream));
+    I->stage_pending[k] = true;
+    return bytes;
+}
+
 void octree_cuc_wait_reads(octree_glc_t* rc)
 {
     Impl* I = impl_of(rc);
-    if (I->ring_on) CUDA_OK(cudaStreamSynchronize(I->copy_stream));
+    if (I->copy_stream) CUDA_OK(cudaStreamSynchronize(I->copy_stream));
 }
 
 void octree_cuc_set_frame_target(octree_glc_t* rc, uint64_t device_ptr, size_t pitch_pixels)

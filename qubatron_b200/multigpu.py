@@ -144,6 +144,21 @@ class ShardedFrame:
             return out
         return host
 
+    def read_frame_async(self, out=None):
+        """COLLECTIVE (call on every rank after assemble()): rank 0 queues the copy of the assembled frame into `out`
+        (page-locked uint8 [H,W,4]) so that it overlaps the next frame; finish with rc.wait_reads() on rank 0.
+        p2p gather: rank 0 snapshots its framebuffer into a staging buffer on the render stream (a few us), then a
+        second fence keeps the other ranks from storing the NEXT frame's tiles into it before that snapshot is
+        taken; the host copy runs from the staging buffer on the copy stream."""
+        if self.world == 1:
+            return self.rc.read_frame_async(out)
+        if self.gather != "p2p":
+            return self.read_frame(out) if self.rank == 0 else None
+        if self.rank == 0:
+            self.rc.read_frame_staged(out)
+        self.dist.all_reduce(self.fence)
+        return out
+
     def broadcast_updates(self, device):
         """Rank 0's pending range uploads -> every rank (rank 0 applies its own at the next frame)."""
         if self.world == 1:

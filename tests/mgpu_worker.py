@@ -49,6 +49,36 @@ def main():
             print("gather=%s world=%d max rgba diff %d" % (gather, world, d), flush=True)
             ok = ok and d <= parity.RGB_TOL
 
+        # pipelined readback (collective): frames alternate between shoot = 0 / 1 while their host copies are in
+        # flight; every host buffer must end up holding ITS frame
+        sync_frames = []
+        for shoot in (0, 1):
+            rc.update(W, H, pos, ang, shoot=shoot)
+            sh.assemble()
+            torch.cuda.synchronize()
+            dist.barrier()
+            sync_frames.append(sh.read_frame().copy() if rank == 0 else None)
+            dist.barrier()
+        bufs = [np.zeros((H, W, 4), np.uint8) for _ in range(2)]
+        for b in bufs:
+            torch.cuda.cudart().cudaHostRegister(b.ctypes.data, b.nbytes, 0)
+        for it in range(8):
+            rc.update(W, H, pos, ang, shoot=it & 1)
+            sh.assemble()
+            sh.read_frame_async(bufs[it & 1] if rank == 0 else None)
+        if rank == 0:
+            rc.wait_reads()
+        torch.cuda.synchronize()
+        dist.barrier()
+        if rank == 0:
+            same = all(np.array_equal(bufs[k], sync_frames[k]) for k in (0, 1))
+            differ = not np.array_equal(sync_frames[0], sync_frames[1])
+            print("gather=%s pipelined readback: buffers hold their frames %s (frames differ %s)" % (gather, same, differ),
+                  flush=True)
+            ok = ok and same and differ
+        for b in bufs:
+            torch.cuda.cudart().cudaHostUnregister(b.ctypes.data)
+
         # zero-and-append on rank 0 only, then broadcast
         tree = S.HostOctree()
         tree.insert_points(sc.pnt_s)
