@@ -1897,13 +1897,15 @@ size_t octree_cuc_skeleton_read_out(octree_glc_t* rc, int32_t* oct14, int32_t* o
     if (oct54) CUDA_OK(cudaMemcpyAsync(oct54, I->skin_p54, n * 16, cudaMemcpyDeviceToHost, st));
     if (oct94) CUDA_OK(cudaMemcpyAsync(oct94, I->skin_p94, n * 16, cudaMemcpyDeviceToHost, st));
     if (pnt_out) CUDA_OK(cudaMemcpyAsync(pnt_out, I->skin_pnt_out, n * 12, cudaMemcpyDeviceToHost, st));
-    if (nrm_out)
+    float* packed = nullptr;
+    if (nrm_out && n)
     {
-        std::vector<float> rec(n * 8);
-        CUDA_OK(cudaMemcpyAsync(rec.data(), I->pts[1].rec.ptr, n * 32, cudaMemcpyDeviceToHost, st));
-        CUDA_OK(cudaStreamSynchronize(st));
-        for (size_t i = 0; i < n; i++)
-            for (int c = 0; c < 3; c++) nrm_out[i * 3 + c] = rec[i * 8 + 4 + c];
+        packed = scratch<float>(I, n * 3);
+        gather_normals_kernel<<<nblk(n), 256, 0, st>>>((const float*) I->pts[1].rec.ptr, n, packed);
+        CUDA_OK(cudaGetLastError());
+        I->launches++;
+        CUDA_OK(cudaMemcpyAsync(nrm_out, packed, n * 12, cudaMemcpyDeviceToHost, st));
+        scratch_free(I, packed);
     }
     CUDA_OK(cudaStreamSynchronize(st));
     return n;

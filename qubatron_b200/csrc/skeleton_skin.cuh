@@ -173,4 +173,14 @@ __global__ void skin_kernel(const SkinParams S, size_t n, const float* __restric
     }
 }
 
+// normals of the first n point records -> float[3n] (the reference's nrm_out buffer)
+__global__ void gather_normals_kernel(const float* __restrict__ rec, size_t n, float* __restrict__ out3)
+{
+    size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out3[i * 3 + 0] = rec[i * 8 + 4];
+    out3[i * 3 + 1] = rec[i * 8 + 5];
+    out3[i * 3 + 2] = rec[i * 8 + 6];
+}
+
 } // namespace qb
