@@ -440,10 +440,30 @@ static void frame_setup(const qb_uniforms* u, frame_consts* fc)
     fc->sy = u->dimensions[1] / (float) u->vp_h;
 }
 
+/* Optional per-pixel `coord` planes ([vp_h][vp_w] floats each).  GL does not require the rasteriser's interpolation of
+ * a varying to be exact, and llvmpipe's is not on every pixel (a few 1e-6 off on some rows / columns of some
+ * viewports): the oracle evaluates coord = pixel centre exactly, and when it is compared against llvmpipe on
+ * tie-prone views (scripts/oracle_fuzz_llvmpipe.py) it is given the coord llvmpipe actually produced (glsl_ref mode
+ * 9), so that the comparison is about the traversal and shading, not about one driver's rasteriser. */
+static const float* g_coord_x = NULL;
+static const float* g_coord_y = NULL;
+static int          g_coord_w = 0;
+void qb_oracle_set_coord_override(const float* cx, const float* cy, int width)
+{
+    g_coord_x = cx;
+    g_coord_y = cy;
+    g_coord_w = width;
+}
+
 static inline f3 pixel_dir(const frame_consts* fc, int px, int py)
 {
     /* L402-404, L412-413 */
     f3 ctp = {((float) px + 0.5f) * fc->sx, ((float) py + 0.5f) * fc->sy, 0.0f};
+    if (g_coord_x)
+    {
+        ctp.x = g_coord_x[(size_t) py * g_coord_w + px];
+        ctp.y = g_coord_y[(size_t) py * g_coord_w + px];
+    }
     f3 csv = {ctp.x - fc->cfp.x, ctp.y - fc->cfp.y, ctp.z - fc->cfp.z};
     csv    = quat_rotate(fc->qz, csv);
     csv    = quat_rotate(fc->qx, csv);

@@ -108,6 +108,10 @@ void qb_oracle_uniforms(qb_uniforms* u, float width, float height, const float p
 void qb_oracle_render(const qb_scene* sc, const qb_uniforms* u, int row0, int row1, uint8_t* rgba, uint8_t* flags,
                       int32_t* aux, qb_counters* counters, int threads);
 
+/* test hook: per-pixel `coord` planes ([vp_h][width] floats) used instead of the exact pixel centres, NULL to clear
+ * (see octree_fsh_oracle.c; for comparisons against a rasteriser whose interpolation is not exact) */
+void qb_oracle_set_coord_override(const float* cx, const float* cy, int width);
+
 /* one cube_trace_line (octree_fsh.c L138-379).  returns 0 = miss (isp = 0),
  * 1 = leaf returned, -1 = discard.  out_isp[4], out_tlf[4], out_nodes[2],
  * out_models[2] may be NULL. */

@@ -205,6 +205,37 @@ def present(frame, u, width, height):
     return out
 
 
+def render_with_coords(oscene, u, coord_x, coord_y, div=DIV_GLSL):
+    """render() with the per-pixel `coord` varying supplied by the caller (float32 [H,W] each) instead of the exact
+    pixel centres -- e.g. the values llvmpipe's rasteriser interpolated (glsl_coords)."""
+    cx = np.ascontiguousarray(coord_x, dtype=np.float32)
+    cy = np.ascontiguousarray(coord_y, dtype=np.float32)
+    assert cx.shape == cy.shape == (u.vp_h, u.vp_w)
+    l = lib(div)
+    l.qb_oracle_set_coord_override.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    l.qb_oracle_set_coord_override(_ptr(cx), _ptr(cy), u.vp_w)
+    try:
+        return render(oscene, u, div=div)
+    finally:
+        l.qb_oracle_set_coord_override(None, None, 0)
+
+
+def glsl_coords(scene, u):
+    """The `coord` varying of every pixel as llvmpipe interpolated it (glsl_ref mode 9): (x, y) float32 [H,W]."""
+    out = []
+    for e in ("coord.x", "coord.y"):
+        os.environ["QB_DEBUG_EXPR"] = e
+        a, _ = glsl_render(scene, u, mode=9)
+        out.append(a.view(np.float32).reshape(u.vp_h, u.vp_w).copy())
+    os.environ.pop("QB_DEBUG_EXPR", None)
+    # a pixel whose primary ray is discarded writes nothing: it reads back as 0 -> use the exact centre there
+    sx, sy = u.dimensions[0] / np.float32(u.vp_w), u.dimensions[1] / np.float32(u.vp_h)
+    ex = ((np.arange(u.vp_w, dtype=np.float32) + np.float32(0.5)) * np.float32(sx))[None, :].repeat(u.vp_h, 0)
+    ey = ((np.arange(u.vp_h, dtype=np.float32) + np.float32(0.5)) * np.float32(sy))[:, None].repeat(u.vp_w, 1)
+    blank = (out[0] == 0) & (out[1] == 0)
+    return np.where(blank, ex, out[0]).astype(np.float32), np.where(blank, ey, out[1]).astype(np.float32)
+
+
 def pixel_rays(u):
     """Primary ray direction of every pixel: float32 [H,W,3]."""
     W, H = u.vp_w, u.vp_h
