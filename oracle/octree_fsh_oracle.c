@@ -408,6 +408,14 @@ typedef struct frame_consts
     float sx, sy;     /* coord scale when the viewport truncates ow/oh */
 } frame_consts;
 
+/* Optional view quaternions qz, qx (xyzw each).  They are the only place where the pixel program calls sin / cos
+ * (quat_from_axis_angle, L406-408), whose precision GLSL ES leaves to the implementation: llvmpipe's polynomial and
+ * libm's sinf / cosf agree to the last bit for most angles and differ by one ulp for some, which moves csv by an ulp
+ * and flips a pixel once in ~10^6.  The oracle (like the connector) evaluates them with libm; when
+ * it is compared against llvmpipe over random views it is given the driver's own two quaternions (glsl_ref mode 9). */
+static const float* g_quat_override = NULL; /* qz[4], qx[4] */
+void                qb_oracle_set_quat_override(const float* qz_qx8) { g_quat_override = qz_qx8; }
+
 static void frame_setup(const qb_uniforms* u, frame_consts* fc)
 {
     /* L403: tan(PI/4.0) folds to 1.0f in fp32 */
@@ -422,6 +430,12 @@ static void frame_setup(const qb_uniforms* u, frame_consts* fc)
     fc->qz   = quat_axis_angle(yaxis, -u->angle_in[0]);
     f3 vx    = quat_rotate(fc->qz, negx);
     fc->qx   = quat_axis_angle(vx, -u->angle_in[1]);
+    if (g_quat_override)
+    {
+        const float* q = g_quat_override;
+        fc->qz         = (f4){q[0], q[1], q[2], q[3]};
+        fc->qx         = (f4){q[4], q[5], q[6], q[7]};
+    }
 
     fc->camfp.x = u->camfp[0];
     fc->camfp.y = u->camfp[1];

@@ -112,6 +112,9 @@ void qb_oracle_render(const qb_scene* sc, const qb_uniforms* u, int row0, int ro
  * (see octree_fsh_oracle.c; for comparisons against a rasteriser whose interpolation is not exact) */
 void qb_oracle_set_coord_override(const float* cx, const float* cy, int width);
 
+/* test hook: the view quaternions qz, qx (8 floats) instead of the libm ones, NULL to clear (octree_fsh_oracle.c) */
+void qb_oracle_set_quat_override(const float* qz_qx8);
+
 /* one cube_trace_line (octree_fsh.c L138-379).  returns 0 = miss (isp = 0),
  * 1 = leaf returned, -1 = discard.  out_isp[4], out_tlf[4], out_nodes[2],
  * out_models[2] may be NULL. */

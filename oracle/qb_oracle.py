@@ -205,19 +205,47 @@ def present(frame, u, width, height):
     return out
 
 
-def render_with_coords(oscene, u, coord_x, coord_y, div=DIV_GLSL):
+def render_with_coords(oscene, u, coord_x, coord_y, div=DIV_GLSL, quats=None):
     """render() with the per-pixel `coord` varying supplied by the caller (float32 [H,W] each) instead of the exact
-    pixel centres -- e.g. the values llvmpipe's rasteriser interpolated (glsl_coords)."""
+    pixel centres -- e.g. the values llvmpipe's rasteriser interpolated (glsl_coords) -- and, optionally, the view
+    quaternions qz, qx (8 floats) as a GL driver's sin / cos produced them (glsl_quats) instead of libm's."""
     cx = np.ascontiguousarray(coord_x, dtype=np.float32)
     cy = np.ascontiguousarray(coord_y, dtype=np.float32)
     assert cx.shape == cy.shape == (u.vp_h, u.vp_w)
     l = lib(div)
     l.qb_oracle_set_coord_override.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    l.qb_oracle_set_quat_override.argtypes = [C.c_void_p]
     l.qb_oracle_set_coord_override(_ptr(cx), _ptr(cy), u.vp_w)
+    q = None if quats is None else np.ascontiguousarray(quats, dtype=np.float32).reshape(8)
+    if q is not None:
+        l.qb_oracle_set_quat_override(_ptr(q))
     try:
         return render(oscene, u, div=div)
     finally:
         l.qb_oracle_set_coord_override(None, None, 0)
+        l.qb_oracle_set_quat_override(None)
+
+
+def glsl_quats(scene, u):
+    """qz, qx of main() (octree_fsh.c L406-408) as llvmpipe evaluates them: float32 [8], None if no pixel survives."""
+    out = []
+    for e in ("qz.x", "qz.y", "qz.z", "qz.w", "qx.x", "qx.y", "qx.z", "qx.w"):
+        os.environ["QB_DEBUG_EXPR"] = e
+        a, _ = glsl_render(scene, u, mode=9)
+        frame, _ = (a, None)
+        v = a.view(np.float32).reshape(-1)
+        raw = a.reshape(-1)
+        live = raw != 0
+        if e == "qz.x":
+            rgba, _ = glsl_render(scene, u, mode=0)
+            alive = (rgba.reshape(-1, 4) != 0).any(axis=1)
+            if not alive.any():
+                os.environ.pop("QB_DEBUG_EXPR", None)
+                return None
+            pick = int(np.nonzero(alive)[0][0])     # a pixel that was not discarded carries the value
+        out.append(v[pick])
+    os.environ.pop("QB_DEBUG_EXPR", None)
+    return np.array(out, dtype=np.float32)
 
 
 def glsl_coords(scene, u):

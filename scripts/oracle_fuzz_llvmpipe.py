@@ -53,7 +53,8 @@ for c in range(cases):
     if diff.max() > 0:
         # not a traversal difference if the oracle, given the coord llvmpipe's rasteriser produced, agrees
         cx, cy = O.glsl_coords(sc, u)
-        ref2 = O.render_with_coords(O.OracleScene(sc), u, cx, cy)
+        quats = O.glsl_quats(sc, u)   # ... and the view quaternions its sin / cos produced
+        ref2 = O.render_with_coords(O.OracleScene(sc), u, cx, cy, quats=quats)
         diff2 = np.abs(rgba.astype(int) - ref2["rgba"].astype(int)).max(axis=2)
         off = float(max(np.abs(cx - (np.arange(W, dtype=np.float32) + 0.5)[None, :]).max(),
                         np.abs(cy - (np.arange(H, dtype=np.float32) + 0.5)[:, None]).max()))
@@ -62,6 +63,7 @@ for c in range(cases):
         out["cases_with_inexact_coord"] += 1
         out["differing_pixels_left_with_llvmpipe_coord"] += int((diff2 > 0).sum())
         print("case", c, "seed", seed0 + c, "differs on", int((diff > 0).sum()), "pixels (max %d);" % int(diff.max()),
-              "llvmpipe's coord is off by up to %.2e;" % off, "with that coord:", int((diff2 > 0).sum()), "differ", flush=True)
+              "llvmpipe's coord is off by up to %.2e;" % off, "with llvmpipe's coord and view quaternions:",
+              int((diff2 > 0).sum()), "differ", flush=True)
 out["seconds"] = round(time.time() - t0, 1)
 print(json.dumps(out))
