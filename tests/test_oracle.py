@@ -122,3 +122,20 @@ def test_rows_and_threads_are_deterministic(scene_random):
     assert a["counters"] == b["counters"]
     top = O.render(osc, u, rows=(24, 48), threads=2)
     assert np.array_equal(top["rgba"][24:], a["rgba"][24:]) and (top["rgba"][:24] == 0).all()
+
+
+def test_coord_override_hook_is_transparent(scene_random):
+    """render_with_coords (the hook the llvmpipe sweep uses to hand the oracle a rasteriser's interpolated `coord`)
+    with the exact pixel centres is the plain render; a shifted coord plane moves the frame."""
+    W, H = 96, 64
+    u = O.uniforms(W, H, (760.0, 200.0, 420.0), (-0.05, -0.12, 0.0))
+    osc = O.OracleScene(scene_random)
+    plain = O.render(osc, u)
+    cx = (np.arange(W, dtype=np.float32) + np.float32(0.5))[None, :].repeat(H, 0)
+    cy = (np.arange(H, dtype=np.float32) + np.float32(0.5))[:, None].repeat(W, 1)
+    same = O.render_with_coords(osc, u, cx, cy)
+    assert np.array_equal(same["rgba"], plain["rgba"]) and np.array_equal(same["aux"], plain["aux"])
+    moved = O.render_with_coords(osc, u, cx + np.float32(3.0), cy)
+    assert np.array_equal(moved["rgba"][:, :-3], plain["rgba"][:, 3:])
+    again = O.render(osc, u)          # the hook is cleared afterwards
+    assert np.array_equal(again["rgba"], plain["rgba"])
