@@ -123,7 +123,9 @@ static void skin_point(const qb_bone_consts* bc, s3 position, s3 normal, const f
     int   corner_count  = 0;
     s3    corner_center = position;
     float tozerow_sum   = 0.0f;
-    corner_normals[0]   = (s3){0.0f, 0.0f, 0.0f}; /* GLSL leaves it undefined when no bone is in range */
+    /* A point out of range of every bone pair takes corner_normals[0] (L172), which the shader never wrote: undefined
+     * in GLSL (garbage on llvmpipe, scripts/oracle_fuzz_tf_llvmpipe.py).  Defined here, and in the connector, as 0. */
+    corner_normals[0] = (s3){0.0f, 0.0f, 0.0f};
 
     for (int k = 0; k < 10; k++)
     {

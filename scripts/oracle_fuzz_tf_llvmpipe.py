@@ -32,9 +32,14 @@ for c in range(cases):
     _, gp, _ = O.glsl_skin(ob, nb, pos, nrm, points=True)
     rot, seen = O.glsl_bone_rotations(ob, nb, pos, nrm)
     d, no, po = O.skin(ob, nb, pos, nrm, rotations=rot)
-    bad = int(((d != gd).any(axis=1) | (bits(no) != bits(gn)).any(axis=1) | (bits(po) != bits(gp)).any(axis=1)).sum())
+    # A point out of range of every bone pair keeps its position and takes `corner_normals[0]`, which the shader never
+    # wrote (skeleton_vsh.c L172): undefined in GLSL, garbage on llvmpipe, 0 in the oracle and the connector.  Its
+    # normal is not compared.
+    loose = (bits(po) == bits(pos)).all(axis=1) & (no == 0).all(axis=1)
+    bad = int(((d != gd).any(axis=1) | ((bits(no) != bits(gn)).any(axis=1) & ~loose) | (bits(po) != bits(gp)).any(axis=1)).sum())
     out["skin_points"] += len(pos)
     out["skin_mismatches"] += bad
+    out["skin_points_out_of_every_bones_range"] = out.get("skin_points_out_of_every_bones_range", 0) + int(loose.sum())
     # ---- particles over a random tree
     levels = int(rng.choice([8, 10, 12]))
     sc = S.make_random(int(rng.integers(2000, 12000)), 0, seed=seed0 + c, levels=levels, clustered=True)

@@ -547,6 +547,36 @@ def test_skinning_pass_equals_the_reference_vertex_program_on_llvmpipe(name):
     rc.destroy()
 
 
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_skinning_pass_random_poses_equal_the_oracle(seed):
+    """Random skeleton poses (every joint jittered, random twists, shrunken radii so that some points are out of
+    range of every bone pair and keep their position with a zero normal), both division modes: bit-exact."""
+    rng = np.random.default_rng(900 + seed)
+    fig_p, _, fig_n = S.zombie_raw(spacing=0.9, shells=3)
+    sel = rng.choice(len(fig_p), 20000, replace=False)
+    pos, nrm = fig_p[sel], fig_n[sel]
+    ob, nb = S.zombie_bones(pose=float(rng.uniform(0, 3)), shift=tuple(rng.normal(0, 8, 3)))
+    nb = nb.copy()
+    nb[:, :3] += rng.normal(0, 2.0, (20, 3)).astype(np.float32)
+    nb[::2, 3] = rng.normal(0, 0.4, 10).astype(np.float32)
+    ob = ob.copy()
+    ob[::2, 3] *= np.float32(0.6)
+    rc = K.OctreeGlc(b"", device=0)
+    rc.skeleton_alloc_in(pos, nrm)
+    loose = 0
+    for div in (K.DIV_GLSL, K.DIV_IEEE):
+        rc.set_division(div)
+        rc.skeleton_update(ob, nb, build_tree=False)
+        digits, nrm_out, pnt_out = rc.skeleton_read_out(len(pos))
+        want_d, want_n, want_p = O.skin(ob, nb, pos, nrm, div=div)
+        assert np.array_equal(digits, want_d)
+        assert np.array_equal(nrm_out.view(np.uint32), want_n.view(np.uint32))
+        assert np.array_equal(pnt_out.view(np.uint32), want_p.view(np.uint32))
+        loose = int(((want_n == 0).all(axis=1) & (want_p == pos).all(axis=1)).sum())
+    assert loose > 0
+    rc.destroy()
+
+
 def test_skin_build_render_on_the_device_equals_the_host_pipeline(scene_c1):
     """The reference's per-frame dynamic-model pipeline (qubatron.c L425-452 + L508-548): skin -> read back ->
     octree_reset + octree_insert_path -> upload tree and normals -> render.  Here all three stages stay on the
