@@ -699,6 +699,25 @@ def test_presentation_pass_equals_the_reference_window_on_llvmpipe(q):
     rc.destroy()
 
 
+def test_presentation_random_windows_equal_the_oracle(scene_random):
+    """Random window sizes and render scales: the connector's window image equals the (llvmpipe-pinned) oracle's
+    presentation of the connector's own frame, byte for byte."""
+    rng = np.random.default_rng(77)
+    rc = K.OctreeGlc(b"", device=0)
+    rc.upload_scene(scene_random)
+    rc.enable_present(True)
+    for _ in range(12):
+        q = int(rng.integers(4, 11))
+        ww, wh = int(rng.integers(120, 900)), int(rng.integers(90, 600))
+        pos, ang = (760.0 + float(rng.normal(0, 20)), 200.0, 420.0), (-0.05 + float(rng.normal(0, 0.2)), -0.12, 0.0)
+        rc.update(ww, wh, pos, ang, quality=q)
+        u = O.uniforms(ww, wh, pos, ang, quality=q)
+        frame = rc.read_frame()
+        assert frame.shape[:2] == (u.vp_h, u.vp_w)
+        assert np.array_equal(rc.read_window(), O.present(frame, u, ww, wh)), (q, ww, wh)
+    rc.destroy()
+
+
 def test_presentation_at_full_size_equals_the_oracle(scene_c1):
     """1080p window at quality 10 (a copy + crosshair) and at quality 7 (2.5x upscale of a 768 x 432 frame)."""
     rc = K.OctreeGlc(b"", device=0)
