@@ -355,6 +355,11 @@ void   octree_cuc_apply_blob(octree_glc_t* rc, const void* blob_host, size_t byt
  * returns the number of results that differ (must be 0) */
 uint64_t octree_cuc_selftest_div(octree_glc_t* rc, uint64_t seed, uint64_t count);
 
+/* host-side copy of the fast kernel's candidate-ordering table (octree_trace_fast.cuh, g_order_lut): 4096
+ * entries, index = the 12 compare bits of the common expansion case, value = ordered candidate list + one-hot
+ * octants.  No device needed; tests rebuild it from the reference's formulation (octree_fsh.c L276-311). */
+void octree_cuc_debug_order_lut(uint64_t* out4096);
+
 /* library self-description */
 const char* octree_cuc_version(void);
 

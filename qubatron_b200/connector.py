@@ -112,6 +112,7 @@ _PROTOS = {
     "octree_cuc_unpin_host_buffer": (None, [C.POINTER(octree_glc_t), C.c_void_p]),
     "octree_cuc_take_upload_ms": (C.c_double, [C.POINTER(octree_glc_t)]),
     "octree_cuc_selftest_div": (C.c_uint64, [C.POINTER(octree_glc_t), C.c_uint64, C.c_uint64]),
+    "octree_cuc_debug_order_lut": (None, [C.c_void_p]),
     "octree_cuc_export_pending": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_void_p, C.c_size_t]),
     "octree_cuc_apply_blob": (None, [C.POINTER(octree_glc_t), C.c_void_p, C.c_size_t]),
     "octree_cuc_version": (C.c_char_p, []),

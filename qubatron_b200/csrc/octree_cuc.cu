@@ -2086,6 +2086,11 @@ uint64_t octree_cuc_selftest_div(octree_glc_t* rc, uint64_t seed, uint64_t count
     return (uint64_t) bad;
 }
 
+void octree_cuc_debug_order_lut(uint64_t* out4096)
+{
+    for (int i = 0; i < ORDER_LUT_SIZE; i++) out4096[i] = (uint64_t) h_order_lut_copy.v[i];
+}
+
 // blob = { uint64 ndesc, uint64 payload_bytes, RangeDesc[ndesc], payload }
 size_t octree_cuc_export_pending(octree_glc_t* rc, void* blob_host, size_t capacity)
 {
