@@ -13,15 +13,13 @@ except Exception as e: print(sys.argv[1],'FAILED',e,flush=True)
 PY
 }
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader
-ab $PWD/ab/liboctree_cuc_v9.so v9
-ab $PWD/qubatron_b200/liboctree_cuc.so v10
+ab $PWD/ab/liboctree_cuc_v10.so v10
+ab $PWD/qubatron_b200/liboctree_cuc.so v11
 echo "== pytest -m gpu"; (time timeout 420 python -m pytest tests -m gpu -x -q) > gpurun_out/pytest_gpu.log 2>&1; tail -5 gpurun_out/pytest_gpu.log
 echo "== parity fuzz"; timeout 150 python scripts/parity_fuzz.py 150 5000 > gpurun_out/fuzz.log 2>&1; tail -3 gpurun_out/fuzz.log
-ab $PWD/ab/liboctree_cuc_v10_mb7.so v10_mb7
-ab $PWD/ab/liboctree_cuc_v9.so v9_again
 echo "== ncu launch list"
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu --no-c1 > gpurun_out/launch_bench.log 2>&1
 echo "== ncu full"
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:render_fast -c 4 -o gpurun_out/prof_v10 -f python scripts/profile_frame.py 1.0 4 > gpurun_out/ncu_full.log 2>&1; tail -2 gpurun_out/ncu_full.log
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:render_fast -c 4 -o gpurun_out/prof_v11 -f python scripts/profile_frame.py 1.0 4 > gpurun_out/ncu_full.log 2>&1; tail -2 gpurun_out/ncu_full.log
 echo "== bench default"; timeout 400 python bench.py > gpurun_out/bench_default.json 2>gpurun_out/bench_default.err; tail -c 600 gpurun_out/bench_default.json
 ls -la gpurun_out
