@@ -1,5 +1,9 @@
 #!/bin/bash
-# A/B of build variants of the hot kernel (ab/*.so, built with -DQB_V11_* switches) + the parity suite on two of them
+# Record of the v11 variant A/B: build variants of the hot kernel in ab/*.so, built with
+# -DQB_V11_SELP / _STORE / _DYNSKIP / _SNAP / -DQB_MINBLOCKS=7 switches (a selp, b dynskip, j selp+snap, k selp+store,
+# h selp+store+snap, i = h + 7 CTAs, f all, g = f + 7 CTAs), + the parity suite on two of them.  The winners
+# (selp, store, 7 CTAs) are the source now and the switches are gone; to A/B a new idea, build it into ab/ with
+# `make OUT=... EXTRA=-D...` and list it here.
 mkdir -p gpurun_out
 ab() { # lib tag
   QB_CUC_LIB=$1 timeout 300 python bench.py --steps 24 --no-cpu --no-c1 2>gpurun_out/ab_$2.err | tail -1 > gpurun_out/ab_$2.json
