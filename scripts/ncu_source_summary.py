@@ -9,13 +9,19 @@ rows = list(csv.reader(open(sys.argv[1])))
 top_n = int(sys.argv[2]) if len(sys.argv) > 2 else 25
 h = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[h]
-data = [r for r in rows[h + 1:] if len(r) >= len(hdr) - 2 and r[0].startswith("0x")]
+# ncu prints the table of a launch twice (and one pair per selected launch): keep the first table only
+data = []
+for r in rows[h + 1:]:
+    if r and r[0] == "Address":
+        break
+    if len(r) >= len(hdr) - 2 and r[0].startswith("0x"):
+        data.append(r)
 ix = {k: i for i, k in enumerate(hdr)}
 N = lambda r, k: int(float(r[ix[k]] or 0))
 tot = sum(N(r, "Instructions Executed") for r in data)
 thr = sum(N(r, "Thread Instructions Executed") for r in data)
 print("kernel:", rows[0][1] if rows[0] else "?")
-print("SASS lines %d, warp instructions %d, thread instructions %d, avg active threads %.2f" % (
+print("first selected launch: SASS lines %d, warp instructions %d, thread instructions %d, avg active threads %.2f" % (
     len(data), tot, thr, thr / max(tot, 1)))
 hist = collections.Counter()
 for r in data:
