@@ -125,6 +125,14 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads():
+    """Host threads this process may use (affinity mask), independent of OMP_NUM_THREADS."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -135,15 +143,25 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic():
-    """dram bytes per launch of the render kernel from the committed ncu capture, if any."""
-    p = os.path.join(ROOT, "profiles", "traffic.json")
+def _profile_json(name):
+    p = os.path.join(ROOT, "profiles", name)
     if os.path.exists(p):
         try:
             return json.load(open(p))
         except Exception:
             return None
     return None
+
+
+def ncu_traffic():
+    """dram bytes per launch of the render kernel from the committed ncu capture, if any (NOT measured by this run:
+    a run under a profiler is never a bench run; the line says where the figure comes from)."""
+    return _profile_json("traffic.json")
+
+
+def ncu_issue():
+    """instruction-issue figures of the render kernel from the committed ncu capture (profiles/issue_roofline.json)."""
+    return _profile_json("issue_roofline.json")
 
 
 # ---------------------------------------------------------------------------
@@ -191,7 +209,9 @@ def reference_arm(args):
         return
     from oracle import qb_oracle as O
     sc, meta = get_scene(args.scale, 0, lambda: None)
-    cores = os.cpu_count() or 1
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the thread count is set explicitly, and the line reports
+    # the number actually used
+    cores = host_threads()
     poses = sc.cameras
     use_ref = O.have_ref()
     step_rays, step_s = [], []
@@ -222,8 +242,8 @@ def reference_arm(args):
             org = np.tile(np.asarray(pos, np.float32), (len(xs), 1))
             light = np.array([u.light[0], u.light[1], u.light[2]], np.float32)
             t = time.time()
-            i_s, tlf_s = ts.trace(org, dirs, threads=0)
-            i_d, tlf_d = td.trace(org, dirs, threads=0)
+            i_s, tlf_s = ts.trace(org, dirs, threads=cores)
+            i_d, tlf_d = td.trace(org, dirs, threads=cores)
             hit = (i_s != 0) | (i_d != 0)
             # shadow ray towards the centre of the hit leaf (the CPU twin returns the leaf cube, not the isp)
             tl = np.where((i_s != 0)[:, None], tlf_s, tlf_d)[hit]
@@ -231,16 +251,17 @@ def reference_arm(args):
             sdir = (tgt - light[None, :]).astype(np.float32)
             sorg = np.tile(light, (len(sdir), 1))
             if len(sdir):
-                ts.trace(sorg, sdir, threads=0)
-                td.trace(sorg, sdir, threads=0)
+                ts.trace(sorg, sdir, threads=cores)
+                td.trace(sorg, sdir, threads=cores)
             dt = time.time() - t
             return len(xs) + len(sdir), dt
         kind, sample = "reference", ("octree_trace_line (oracle/_ref, octree.c unmodified), %d sampled pixels/step "
-                                     "(8x4 patches): primary + shadow ray, static and dynamic tree each, "
-                                     "OpenMP over rays" % nsample)
+                                     "(8x4 patches): primary + shadow ray (aimed at the hit leaf's centre: the CPU "
+                                     "twin returns the leaf cube, not the hit point), static and dynamic tree each, "
+                                     "OpenMP over rays, %d threads" % (nsample, cores))
     else:
         def one_step(i):
-            return cpu_port_bands(sc, poses[i % len(poses)], args.cpu_rows, 0)
+            return cpu_port_bands(sc, poses[i % len(poses)], args.cpu_rows, cores)
         kind, sample = "port", "oracle restatement, %d rows of the 1080p frame per step, OpenMP over rows" % args.cpu_rows
     for i in range(args.warmup):
         one_step(i)
@@ -281,7 +302,7 @@ def c1_llvmpipe():
         return {"renderer": info["renderer"], "rays_per_frame": rays, "first_frame_s": info["frame_s"][0],
                 "frame_s": steady, "mrays_s": rays / steady / 1e6, "threads": "LP_NUM_THREADS default (= cores, max 16)",
                 "frame_s_1_thread": info1["frame_s"][-1], "mrays_s_1_thread": rays / info1["frame_s"][-1] / 1e6,
-                "cores": os.cpu_count()}
+                "cores": host_threads()}
     except Exception as e:  # the baseline is reported, never fatal
         return {"unavailable": repr(e)[:300]}
 
@@ -308,47 +329,23 @@ def c1_gpu(K, device):
             "note": "1 M-point cloud, 640x360, octree (28 MB) is L2-resident; kernel time, CUDA events"}
 
 
-def c5_views(rc, sc, rank, world, dev, dist, torch):
-    """BASELINE configs[4]: 64 views with random (incoherent) cameras on the same level, whole views sharded
-    across the ranks (no exchange at all), one octree_cuc_update_views launch per rank."""
-    rng = np.random.default_rng(777)
-    n = 64
-    pos = np.stack([rng.uniform(150, 1650, n), rng.uniform(90, 330, n), rng.uniform(150, 1650, n)], axis=1)
-    ang = np.stack([rng.uniform(0, 2 * np.pi, n), rng.uniform(-0.6, 0.6, n), np.zeros(n)], axis=1)
-    mine = list(range(rank, n, world))
-    rc.set_frame_target(0, 0)
-    rc.set_shard(0, 1, TILE, TILE)
-    rc.enable_counters(True)
-    rc.update_views(WIDTH, HEIGHT, pos[mine], ang[mine], 0.0, 10, MAXLEVEL, BASESIZE, 0)
-    c = rc.read_counters()
-    rc.enable_counters(False)
-    rays = torch.tensor([c["rays_primary"] + c["rays_shadow"] + c["rays_disc"]], dtype=torch.int64, device=dev)
-    ms = []
-    for _ in range(3):
-        rc.update_views(WIDTH, HEIGHT, pos[mine], ang[mine], 0.0, 10, MAXLEVEL, BASESIZE, 0)
-        ms.append(rc.last_frame_ms())
-    t = torch.tensor([float(np.median(ms))], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(rays)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return {"views": n, "views_per_gpu": len(mine), "rays": int(rays.item()), "batch_ms": float(t.item()),
-            "ms_per_view": float(t.item()) / n, "mrays_s": int(rays.item()) / float(t.item()) / 1e3,
-            "note": "device time of the slowest rank for its share of the 64 views (1080p each)"}
-
-
 def bench_config(meta, args, world):
     return {"workload": "C2: %s -- %d static points (%d octree nodes) + %d dynamic points (%d nodes), depth %d, "
                         "cube %.0f, %dx%d primary+shadow(+light-disc) frame, %d camera poses cycled"
                         % (meta["name"], meta["static_points"], meta["static_nodes"], meta["dynamic_points"],
                            meta["dynamic_nodes"], MAXLEVEL, BASESIZE, WIDTH, HEIGHT, len(meta["cameras"])),
             "scale": args.scale, "width": WIDTH, "height": HEIGHT, "maxlevel": MAXLEVEL,
-            "parallelism": "image tiles %dx%d interleaved over %d GPU(s), octree replicated" % (args.tile, args.tile, world),
+            "parallelism": "image tiles %dx%d interleaved over %d GPU(s), octree replicated; tiles go into rank 0's "
+                           "framebuffer by peer stores from the render kernel, completion by device-side flags "
+                           "(gather=%s)" % (args.tile, args.tile, world, args.gather),
             "tile_order": "heaviest first, from the tile costs measured the last time the same view was rendered "
                           "(each of the cycled poses is first seen in warm-up); the ordering kernel runs inside the "
-                          "timed step; QB_TILE_FEEDBACK=0 renders tiles in image order",
-            "l2": "flushed before every step (256 MiB memset, outside the step's event pair); scene arrays "
-                  "(%.1f GB) also exceed L2" % ((meta["static_nodes"] + meta["dynamic_nodes"]) * 36e-9
-                                                + (meta["static_points"] + meta["dynamic_points"]) * 32e-9)}
+                          "timed step; extras.tile_feedback_off and extras.moving_camera give the figures without it",
+            "l2": "flushed before every step of every leg, e2e included (256 MiB memset, outside the step's event "
+                  "pair; the e2e leg subtracts its measured cost); scene arrays (%.1f GB) also exceed L2; "
+                  "extras.warm_l2 is the same loop without the flush"
+                  % ((meta["static_nodes"] + meta["dynamic_nodes"]) * 36e-9
+                     + (meta["static_points"] + meta["dynamic_points"]) * 32e-9)}
 
 
 # ---------------------------------------------------------------------------
@@ -391,6 +388,309 @@ def main():
     OUT = None
 
 
+def rays_of(c):
+    return c["rays_primary"] + c["rays_shadow"] + c["rays_disc"]
+
+
+class Rig:
+    """Everything a leg of the bench needs: the connector of this rank, its stream, the frame assembly of the
+    world, and the shared timing rules (L2 flush before every step, CUDA events on the launch stream, max over
+    ranks step by step)."""
+
+    def __init__(self, args, torch, dist, K, multigpu, rc, stream, dev, rank, world):
+        self.args, self.torch, self.dist, self.K, self.multigpu = args, torch, dist, K, multigpu
+        self.rc, self.stream, self.dev, self.rank, self.world = rc, stream, dev, rank, world
+        self.flush_buf = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        self.sharded = None
+        self.w = self.h = 0
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+
+    def flush(self):
+        if self.flush_buf is not None:
+            self.flush_buf.fill_(1)
+
+    def shard(self, width, height):
+        """(re)build the frame assembly for a frame size"""
+        if self.sharded is not None:
+            self.sharded.close()
+        self.w, self.h = width, height
+        self.sharded = self.multigpu.ShardedFrame(self.rc, width, height, self.rank, self.world, self.dev,
+                                                  gather=self.args.gather, tile=self.args.tile)
+
+    def unshard(self):
+        if self.sharded is not None:
+            self.sharded.close()
+            self.sharded = None
+        self.rc.set_frame_target(0, 0)
+        self.rc.set_shard(0, 1, self.args.tile, self.args.tile)
+
+    def frame(self, view, shoot=0):
+        pos, ang = view
+        self.rc.update(self.w, self.h, pos, ang, 0.0, 10, MAXLEVEL, BASESIZE, shoot)
+        self.sharded.assemble()
+
+    def max_over_ranks(self, values):
+        t = self.torch.tensor(values, dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.cpu().numpy()
+
+    def sum_over_ranks(self, values):
+        t = self.torch.tensor(values, dtype=self.torch.int64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t)
+        return [int(v) for v in t.tolist()]
+
+    def count(self, views):
+        """work counters of each view's frame (counting instantiation of the kernel, never inside a timed region)"""
+        self.rc.enable_counters(True)
+        out = []
+        for v in views:
+            self.frame(v)
+            c = self.rc.read_counters()
+            keys = sorted(c)
+            out.append(dict(zip(keys, self.sum_over_ranks([c[k] for k in keys]))))
+        self.rc.enable_counters(False)
+        return out
+
+    def timed(self, views, steps, warmup=0, flush=True, before=None):
+        """steps frames cycling through `views`: per-step device time (ms, max over ranks) between events on the
+        launch stream; `before(i)` runs inside the step's event pair ahead of the frame (per-frame updates)."""
+        torch = self.torch
+        for i in range(warmup):
+            if flush:
+                self.flush()
+            if before:
+                before(i)
+            self.frame(views[i % len(views)])
+        torch.cuda.synchronize()
+        self.barrier()
+        if steps == 0:
+            return np.zeros(0)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for i in range(steps):
+            if flush:
+                self.flush()
+            ev[i][0].record(self.stream)
+            if before:
+                before(i)
+            self.frame(views[i % len(views)])
+            ev[i][1].record(self.stream)
+        torch.cuda.synchronize()
+        self.barrier()
+        return self.max_over_ranks([a.elapsed_time(b) for a, b in ev])
+
+    def kernel_ms(self, views, n):
+        """the connector's own event pair around the render kernel alone (max over ranks), L2 flushed"""
+        ms = []
+        for i in range(n):
+            self.flush()
+            self.frame(views[i % len(views)])
+            ms.append(self.rc.last_frame_ms())
+        return self.max_over_ranks(ms)
+
+    def crc_frames(self, views):
+        """CRC32 of rank 0's assembled HOST frame of every view (None on other ranks)"""
+        import zlib
+        out = []
+        for v in views:
+            self.frame(v)
+            self.torch.cuda.synchronize()
+            self.barrier()
+            out.append(zlib.crc32(self.sharded.read_frame().tobytes()) if self.rank == 0 else None)
+            self.barrier()
+        return out
+
+
+def leg_e2e(rig, poses, per_pose, steps):
+    """The reference-facing call with HOST buffers: pose in (pinned constants, H2D inside octree_glc_update), frame
+    out (D2H into page-locked host memory) EVERY step; frame i's copy overlaps the rendering of frame i+1.  Same
+    policy at every N: L2 flushed before each step, the flush's own cost measured and subtracted."""
+    torch, rc, rank, world = rig.torch, rig.rc, rig.rank, rig.world
+    host_frames = None
+    if rank == 0:
+        host_frames = [np.empty((rig.h, rig.w, 4), dtype=np.uint8) for _ in range(2)]
+        for hf in host_frames:
+            torch.cuda.cudart().cudaHostRegister(hf.ctypes.data, hf.nbytes, 0)
+
+    def loop(n):
+        for i in range(n):
+            rig.flush()
+            rig.frame(poses[i % len(poses)])
+            rig.sharded.read_frame_async(host_frames[i & 1] if rank == 0 else None)
+        if rank == 0:
+            rc.wait_reads()
+        torch.cuda.synchronize()
+        rig.barrier()
+
+    loop(3)
+    t = time.time()
+    loop(steps)
+    e2e_s = time.time() - t
+    tf = 0.0
+    if rig.flush_buf is not None:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(rig.stream)
+        for _ in range(steps):
+            rig.flush()
+        b.record(rig.stream)
+        torch.cuda.synchronize()
+        tf = float(rig.max_over_ranks([a.elapsed_time(b)])[0]) / 1e3
+    rays = sum(rays_of(per_pose[i % len(poses)]) for i in range(steps))
+    if rank == 0:
+        for hf in host_frames:
+            torch.cuda.cudart().cudaHostUnregister(hf.ctypes.data)
+    return {"value": rays / max(e2e_s - tf, 1e-9) / 1e6, "unit": UNIT, "h2d_bytes_per_step": 88 * world,
+            "d2h_bytes_per_step": rig.w * rig.h * 4, "ms_per_step": 1e3 * (e2e_s - tf) / steps,
+            "note": "wall clock over the loop minus the measured cost of the L2 flushes (same policy at every N); "
+                    "frame i's copy to page-locked host memory overlaps the rendering of frame i+1"}
+
+
+def camera_path(start, frames=60):
+    """A walking camera: small per-frame deltas from the start pose and one cut half-way (to the last bench pose)."""
+    (px, py, pz), (ax, ay, _) = start
+    out = []
+    for f in range(frames // 2):
+        out.append(((px + 0.35 * f, py + 0.02 * f, pz + 0.2 * f), (ax + 0.004 * f, ay - 0.001 * f, 0.0)))
+    return out
+
+
+def leg_moving_camera(rig, poses):
+    """Tile feedback away from the cached poses: 60 frames, every view new (the exact-view cache never hits, only
+    the most-recent-order fallback applies), feedback on vs off."""
+    path = camera_path(poses[0]) + camera_path(poses[3])
+    c = rig.count(path)
+    rays = sum(rays_of(x) for x in c)
+    out = {"frames": len(path), "rays": rays,
+           "path": "30 frames walking from pose 0, a cut, 30 frames walking from pose 3; every view is new"}
+    for on in (1, 0):
+        rig.rc.set_tile_feedback(on)
+        ms = rig.timed(path, len(path), warmup=0)
+        out["feedback_%s" % ("on" if on else "off")] = {"ms_per_frame": float(ms.mean()), "mrays_s": rays / float(ms.sum()) / 1e3}
+    rig.rc.set_tile_feedback(1)
+    return out
+
+
+def leg_c5(rig, sc, n=64):
+    """BASELINE configs[4]: 64 views with random (incoherent) cameras on the same level, whole views sharded across
+    the ranks (no exchange at all), one octree_cuc_update_views launch per rank."""
+    rc, rank, world = rig.rc, rig.rank, rig.world
+    rng = np.random.default_rng(777)
+    pos = np.stack([rng.uniform(150, 1650, n), rng.uniform(90, 330, n), rng.uniform(150, 1650, n)], axis=1)
+    ang = np.stack([rng.uniform(0, 2 * np.pi, n), rng.uniform(-0.6, 0.6, n), np.zeros(n)], axis=1)
+    mine = list(range(rank, n, world))
+    rig.unshard()
+    rc.enable_counters(True)
+    rc.update_views(1920, 1080, pos[mine], ang[mine], 0.0, 10, MAXLEVEL, BASESIZE, 0)
+    c = rc.read_counters()
+    rc.enable_counters(False)
+    rays = rig.sum_over_ranks([rays_of(c)])[0]
+    ms = []
+    for _ in range(3):
+        rig.flush()
+        rc.update_views(1920, 1080, pos[mine], ang[mine], 0.0, 10, MAXLEVEL, BASESIZE, 0)
+        ms.append(rc.last_frame_ms())
+    t = float(rig.max_over_ranks([float(np.median(ms))])[0])
+    import zlib
+    frames = rc.read_frame(views=len(mine))
+    crcs = [zlib.crc32(frames[k * 1080:(k + 1) * 1080].tobytes()) for k in range(len(mine))]
+    # a checksum of checksums over all 64 views, identical at every N
+    allc = [0] * n
+    for k, v in zip(mine, crcs):
+        allc[k] = v
+    allc = rig.sum_over_ranks(allc)
+    return {"views": n, "views_per_gpu": len(mine), "rays": rays, "batch_ms": t, "ms_per_view": t / n,
+            "mrays_s": rays / t / 1e3, "crc32_of_view_crcs": zlib.crc32(np.asarray(allc, np.uint32).tobytes()),
+            "note": "device time of the slowest rank for its share of the 64 views (1080p each), L2 flushed"}
+
+
+def leg_c4(rig, sc, poses, frames=8):
+    """BASELINE configs[3]: per frame the ~10 M-point figure is re-skinned and its octree rebuilt
+    (octree_cuc_skeleton_update(build_tree=1), every rank for itself: the inputs are 160 floats), a punch-hole batch
+    (~500 zeroed leaves + ~500 re-inserted points -> the engine's per-node 48-byte uploads, issued from C through
+    octree_glc_upload_texbuffer_data, + one colour sub-range) reaches rank 0 and is broadcast as one blob (NCCL),
+    then the 1080p frame.  Time split per frame, device events on the launch stream, max over ranks."""
+    from qubatron_b200 import scene as S
+    torch, rc, rank, world, K = rig.torch, rig.rc, rig.rank, rig.world, rig.K
+    by = float(S._terrain_height(np.float32(760.0), np.float32(230.0)))
+    bones = [S.zombie_bones(base=(760.0, by, 230.0), pose=p, shift=(2.0 * p, 0.0, -1.0 * p))
+             for p in (0.3, 0.8, 1.3, 1.8)]
+    rc.skeleton_alloc_in(np.asarray(sc.pnt_d), np.asarray(sc.nrm_d))
+    stat, col_s, xs_sorted, rng = None, None, None, np.random.default_rng(4)
+    if rank == 0:
+        stat = S.HostOctree()
+        stat.adopt(np.asarray(sc.oct_s))
+        col_s = np.array(sc.col_s)
+        xs_sorted = np.maximum.accumulate(np.asarray(sc.pnt_s[:, 0]))
+
+    def edit(f):
+        """host side of a shot (modelutil_punch_hole, modelutil.c L429-546): untimed, it is the engine's work"""
+        centre = np.array([760.0 + 3 * f, 62.0, 300.0], np.float32)
+        lo_i = int(np.searchsorted(xs_sorted, centre[0] - 30.0))
+        hi_i = int(np.searchsorted(xs_sorted, centre[0] + 30.0))
+        slab = np.asarray(sc.pnt_s[lo_i:hi_i])
+        cand = lo_i + np.nonzero(np.linalg.norm(slab - centre[None, :], axis=1) < 30.0)[0]
+        victims = cand[rng.permutation(len(cand))[:500]] if len(cand) else []
+        edits, touched = [], []
+        for v in victims:
+            m, o = stat.remove_point(sc.pnt_s[v])
+            if o >= 0:
+                edits.append(o)
+                touched.append(m)
+        for m in touched:
+            newp = np.clip((np.asarray(sc.pnt_s[m]) + rng.normal(0, 2.0, 3)).astype(np.float32), 1.0, 1798.0)
+            edits.extend(int(j) for j in stat.insert_point(newp, m) if j > 0)
+            col_s[m] += 0.2
+        return edits, touched
+
+    rows = []
+    pose = poses[0]
+    for f in range(frames + 2):
+        edits, touched = edit(f) if rank == 0 else ([], [])
+        torch.cuda.synchronize()
+        rig.barrier()
+        rig.flush()
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        t0 = time.time()
+        e[0].record(rig.stream)
+        nodes = rc.skeleton_update(*bones[f % len(bones)], build_tree=True)
+        e[1].record(rig.stream)
+        th = time.time()
+        if rank == 0:
+            stat.upload_node_ranges(rc, edits, K.STATIC_OCTREE)          # the engine's loop, in C
+            if touched:
+                rc.upload_points(col_s, K.STATIC_COLOR, min(touched), max(touched) + 1)
+        t_calls = time.time() - th
+        e[2].record(rig.stream)
+        blob_bytes = rig.sharded.broadcast_updates(rig.dev)
+        e[3].record(rig.stream)
+        rig.frame(pose, shoot=1)
+        e[4].record(rig.stream)
+        torch.cuda.synchronize()
+        wall = time.time() - t0
+        rig.barrier()
+        d = [e[i].elapsed_time(e[i + 1]) for i in range(4)]
+        if f >= 2:
+            rows.append(d + [e[0].elapsed_time(e[4]), 1e3 * wall, 1e3 * t_calls, len(edits), blob_bytes, nodes,
+                             rc.last_frame_ms()])
+    a = np.array(rows, dtype=np.float64)
+    mx = rig.max_over_ranks(list(np.median(a[:, :7], axis=0)))
+    import zlib
+    crc = zlib.crc32(rig.sharded.read_frame().tobytes()) if rank == 0 else None
+    rig.barrier()
+    return {"frames": frames, "dynamic_points": int(len(sc.pnt_d)), "dynamic_nodes": int(np.median(a[:, 9])),
+            "node_ranges_per_frame": int(np.median(a[:, 7])), "blob_bytes_per_frame": int(np.median(a[:, 8])),
+            "skin_and_build_ms": float(mx[0]), "range_upload_calls_ms": float(mx[1]),
+            "range_upload_calls_host_ms": float(mx[6]), "broadcast_and_apply_ms": float(mx[2]),
+            "render_ms": float(mx[3]), "render_kernel_ms": float(rig.max_over_ranks([float(np.median(a[:, 10]))])[0]),
+            "frame_ms": float(mx[4]), "frame_wall_ms": float(mx[5]), "last_frame_crc32": crc,
+            "note": "medians over the frames, max over ranks; 1080p, pose 0, L2 flushed before every frame; the "
+                    "reference runs the rebuild on the CPU (10 M x 12 sequential inserts) and uploads 208 MB"}
+
+
 def _main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -399,7 +699,7 @@ def _main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--scale", type=float, default=1.0, help="1.0 = the full 90M-point level")
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic, 2 fast")
-    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"])
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "p2p_nccl", "nccl"])
     ap.add_argument("--division", type=int, default=0, help="0 GLSL a*(1/b) (reference shader on llvmpipe), 1 IEEE")
     ap.add_argument("--cpu-rows", type=int, default=24, help="rows of the frame the cpu_baseline sample renders")
     ap.add_argument("--ref-pixels", type=int, default=65536)
@@ -408,9 +708,9 @@ def _main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--no-c1", action="store_true", help="skip the configs[0] (C1, 640x360) side measurement")
-    ap.add_argument("--c5", action="store_true", help="also measure configs[4]: 64 random views sharded by view")
+    ap.add_argument("--no-extras", action="store_true", help="only the headline legs (value, roofline, e2e)")
     ap.add_argument("--res", default="1080p", choices=["1080p", "4k"],
-                    help="4k = BASELINE configs[2] (3840x2160, tile split); the default is the metric's 1080p")
+                    help="4k = BASELINE configs[2] as the headline; the default is the metric's 1080p")
     args = ap.parse_args()
 
     global DIVISION, WIDTH, HEIGHT, METRIC
@@ -423,6 +723,7 @@ def _main():
 
     import torch
     import torch.distributed as dist
+    import zlib
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -438,6 +739,7 @@ def _main():
             dist.barrier()
 
     from qubatron_b200 import connector as K
+    from qubatron_b200 import multigpu
     sc, meta = get_scene(args.scale, rank, barrier)
     poses = sc.cameras
 
@@ -452,214 +754,157 @@ def _main():
     log("rank %d: scene uploaded in %.1f s, device memory %.2f GB" % (rank, time.time() - t0, rc.memsize / 1e9))
     rc.set_kernel(args.kernel)
     rc.set_division(args.division)
+    rig = Rig(args, torch, dist, K, multigpu, rc, stream, dev, rank, world)
 
-    def render(i):
-        pos, ang = poses[i % len(poses)]
-        rc.update(WIDTH, HEIGHT, pos, ang, 0.0, 10, MAXLEVEL, BASESIZE, 0)
-
-    # frame assembly for N > 1 (qubatron_b200/multigpu.py): peer stores into rank 0's framebuffer, or NCCL reduce
-    from qubatron_b200 import multigpu
-    sharded = multigpu.ShardedFrame(rc, WIDTH, HEIGHT, rank, world, dev, gather=args.gather, tile=args.tile)
-    assemble = sharded.assemble
+    # ---- the frames themselves: CRC32 of rank 0's assembled host frame of every pose, checked against the same
+    # frames rendered unsharded on rank 0 in this run, and against the file a N = 1 run left beside the scene cache
+    crc_key = "%dx%d_div%d_k%d" % (WIDTH, HEIGHT, args.division, args.kernel)
+    crc_path = os.path.join(_cache_dir(args.scale), "frame_crc_%s.json" % crc_key)
+    whole = []
+    if rank == 0:
+        rc.set_shard(0, 1, args.tile, args.tile)
+        for pos, ang in poses:
+            rc.update(WIDTH, HEIGHT, pos, ang, 0.0, 10, MAXLEVEL, BASESIZE, 0)
+            whole.append(zlib.crc32(rc.read_frame().tobytes()))
+    barrier()
+    rig.shard(WIDTH, HEIGHT)
+    frame_crc = rig.crc_frames(poses)
+    crc_info = None
+    if rank == 0:
+        cached = json.load(open(crc_path)) if os.path.exists(crc_path) else None
+        crc_info = {"by_pose": frame_crc, "equal_unsharded_render_on_rank0": frame_crc == whole,
+                    "equal_cached_n1_run": (frame_crc == cached) if cached is not None else None}
+        if frame_crc != whole or (cached is not None and frame_crc != cached):
+            raise SystemExit("bench: frames assembled from %d ranks differ from the single-GPU frames: %r vs %r / %r"
+                             % (world, frame_crc, whole, cached))
+        if world == 1:
+            with open(crc_path + ".tmp", "w") as fh:
+                json.dump(frame_crc, fh)
+            os.replace(crc_path + ".tmp", crc_path)
 
     # ---- per-pose work counters (counting instantiation, outside the timed region) ----
-    rc.enable_counters(True)
-    per_pose = []
-    for i in range(len(poses)):
-        render(i)
-        c = rc.read_counters()
-        t = torch.tensor([c[k] for k in sorted(c)], dtype=torch.int64, device=dev)
-        if world > 1:
-            dist.all_reduce(t)
-        per_pose.append(dict(zip(sorted(c), [int(v) for v in t.tolist()])))
-    rc.enable_counters(False)
+    per_pose = rig.count(poses)
     kernel_used = rc.last_kernel()
 
-    def rays_of(c):
-        return c["rays_primary"] + c["rays_shadow"] + c["rays_disc"]
+    def alg_bytes(c, w=WIDTH, h=HEIGHT):
+        return 32 * (c["expand_s"] + c["expand_d"]) + 4 * (c["leaf_s"] + c["leaf_d"]) + 24 * c["hits"] + 4 * w * h
 
-    def alg_bytes(c):
-        return 32 * (c["expand_s"] + c["expand_d"]) + 4 * (c["leaf_s"] + c["leaf_d"]) + 24 * c["hits"] + 4 * WIDTH * HEIGHT
-
-    flush_buf = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
-    def flush():
-        if flush_buf is not None:
-            flush_buf.fill_(1)
-
-    # ---- warm-up -------------------------------------------------------------------
-    for i in range(args.warmup):
-        flush()
-        render(i)
-        assemble()
-    torch.cuda.synchronize()
-    barrier()
-
-    # ---- timed region: K steps, device-timed per step (events on the launch stream) ----
+    # ---- timed region: K steps after W warm-up steps, device-timed per step (events on the launch stream) ----
+    rig.timed(poses, 0, warmup=args.warmup)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     launches0 = rc.launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kern_ms = []
-    torch.cuda.synchronize()
-    barrier()
     wall0 = time.time()
-    for i in range(args.steps):
-        flush()
-        ev[i][0].record(stream)
-        render(i)
-        assemble()
-        ev[i][1].record(stream)
-        kern_ms.append(None)
-    torch.cuda.synchronize()
-    barrier()
+    step_ms = rig.timed(poses, args.steps)
     wall = time.time() - wall0
-    step_ms = torch.tensor([a.elapsed_time(b) for a, b in ev], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(step_ms, op=dist.ReduceOp.MAX)  # max over ranks, step by step
-    step_ms = step_ms.cpu().numpy()
     launches = rc.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
 
     # kernel-only duration for the roofline: the connector's own event pair brackets just the render kernel
-    kms = []
-    for i in range(min(args.steps, 12)):
-        flush()
-        render(i)
-        kms.append((i % len(poses), rc.last_frame_ms()))
-    kt = torch.tensor([m for _, m in kms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(kt, op=dist.ReduceOp.MAX)
-    kt = kt.cpu().numpy()
+    nk = min(args.steps, 12)
+    kt = rig.kernel_ms(poses, nk)
+    kposes = [i % len(poses) for i in range(nk)]
 
-    # ---- e2e: the reference-facing call with host buffers: pose in (pinned constants H2D inside
-    # octree_glc_update), frame out (D2H into host memory) every step
-    e2e = None
-    if world == 1:
-        # two page-locked host frames: the copy of frame i (octree_cuc_read_frame_async, own copy stream, second
-        # device framebuffer) overlaps the rendering of frame i+1; every step still moves its frame to the host
-        host_frames = [np.empty((HEIGHT, WIDTH, 4), dtype=np.uint8) for _ in range(2)]
-        for hf in host_frames:
-            torch.cuda.cudart().cudaHostRegister(hf.ctypes.data, hf.nbytes, 0)
-        host_frame = host_frames[0]
-        for i in range(3):
-            render(i)
-            rc.read_frame_async(host_frames[i & 1])
-        rc.wait_reads()
-        torch.cuda.synchronize()
-        t = time.time()
-        for i in range(args.steps):
-            flush()
-            render(i)
-            rc.read_frame_async(host_frames[i & 1])
-        rc.wait_reads()
-        torch.cuda.synchronize()
-        e2e_s = time.time() - t
-        e2e_rays = sum(rays_of(per_pose[i % len(poses)]) for i in range(args.steps))
-        # the flush is not part of the call: subtract its measured cost
-        tf = 0.0
-        if flush_buf is not None:
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(stream)
-            for _ in range(args.steps):
-                flush()
-            b.record(stream)
-            torch.cuda.synchronize()
-            tf = a.elapsed_time(b) / 1e3
-        e2e = {"value": e2e_rays / max(e2e_s - tf, 1e-9) / 1e6, "unit": UNIT, "h2d_bytes_per_step": 88,
-               "d2h_bytes_per_step": int(host_frame.nbytes), "ms_per_step": 1e3 * (e2e_s - tf) / args.steps}
-        e2e["note"] = "frame i's device-to-host copy overlaps the rendering of frame i+1 (read_frame_async)"
-        for hf in host_frames:
-            torch.cuda.cudart().cudaHostUnregister(hf.ctypes.data)
-    else:
-        # rank 0 reads the assembled frame back EVERY step into one of two page-locked host frames; the copy of
-        # frame i (device-to-device into a staging buffer after the fence, then to the host on the copy stream)
-        # overlaps the rendering of frame i+1
-        if rank == 0:
-            host_frames = [np.empty((HEIGHT, WIDTH, 4), dtype=np.uint8) for _ in range(2)]
-            for hf in host_frames:
-                torch.cuda.cudart().cudaHostRegister(hf.ctypes.data, hf.nbytes, 0)
-        for i in range(3):
-            render(i)
-            assemble()
-            sharded.read_frame_async(host_frames[i & 1] if rank == 0 else None)
-        if rank == 0:
-            rc.wait_reads()
-        torch.cuda.synchronize()
-        barrier()
-        t = time.time()
-        for i in range(args.steps):
-            render(i)
-            assemble()
-            sharded.read_frame_async(host_frames[i & 1] if rank == 0 else None)
-        if rank == 0:
-            rc.wait_reads()
-        torch.cuda.synchronize()
-        barrier()
-        e2e_s = time.time() - t
-        e2e_rays = sum(rays_of(per_pose[i % len(poses)]) for i in range(args.steps))
-        e2e = {"value": e2e_rays / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": 88 * world,
-               "d2h_bytes_per_step": WIDTH * HEIGHT * 4, "ms_per_step": 1e3 * e2e_s / args.steps,
-               "note": "no L2 flush in this leg; frame i's copy to the host overlaps the rendering of frame i+1"}
-        if rank == 0:
-            for hf in host_frames:
-                torch.cuda.cudart().cudaHostUnregister(hf.ctypes.data)
+    e2e = leg_e2e(rig, poses, per_pose, args.steps)
 
-    c5 = None
-    if args.c5:
-        sharded.close()
-        c5 = c5_views(rc, sc, rank, world, dev, dist, torch)
+    extras = {}
+    if not args.no_extras:
+        t_extras = time.time()
+        warm = rig.timed(poses, args.steps, warmup=2, flush=False)
+        extras["warm_l2"] = {"ms_per_step": float(warm.mean()),
+                             "mrays_s": sum(rays_of(per_pose[i % len(poses)]) for i in range(args.steps)) / float(warm.sum()) / 1e3,
+                             "note": "the timed loop without the L2 flush: the 4 poses' working set (~100 MB of "
+                                     "DRAM traffic) stays L2-resident, as it does for a camera that moves slowly"}
+        rc.set_tile_feedback(0)
+        off = rig.timed(poses, args.steps, warmup=2)
+        rc.set_tile_feedback(1)
+        extras["tile_feedback_off"] = {"ms_per_step": float(off.mean()), "note": "tiles in image order (QB_TILE_FEEDBACK=0)"}
+        extras["moving_camera"] = leg_moving_camera(rig, poses)
+        if WIDTH == 1920:
+            # configs[2]: the same level at 3840x2160 by image tiles
+            rig.shard(3840, 2160)
+            c4k = rig.count(poses)
+            crc4k = rig.crc_frames(poses)
+            ms4k = rig.timed(poses, 12, warmup=len(poses))
+            rays4k = sum(rays_of(c4k[i % len(poses)]) for i in range(12))
+            k4 = rig.kernel_ms(poses, 8)
+            b4 = sum(alg_bytes(c4k[i % len(poses)], 3840, 2160) for i in range(8))
+            extras["c3_2160p"] = {"ms_per_step": float(ms4k.mean()), "mrays_s": rays4k / float(ms4k.sum()) / 1e3,
+                                  "frame_crc32_by_pose": crc4k, "kernel_ms_mean": float(k4.mean()),
+                                  "roofline_frac": b4 / (float(k4.sum()) / 1e3) / 1e9 / (measured_peak()[0] * world),
+                                  "note": "BASELINE configs[2]: 3840x2160, 12 steps over the 4 poses, L2 flushed"}
+            extras["c5_64_views"] = leg_c5(rig, sc)
+            rig.shard(WIDTH, HEIGHT)
+            extras["c4_dynamic_scene"] = leg_c4(rig, sc, poses)      # last: it edits the level
+        extras["extras_wall_s"] = time.time() - t_extras
 
     if rank == 0:
         total_rays = sum(rays_of(per_pose[i % len(poses)]) for i in range(args.steps))
         total_ms = float(step_ms.sum())
         value = total_rays / total_ms / 1e3
         peak, peak_src = measured_peak()
-        # roofline of the render kernel: algorithmic bytes of the frames timed / their kernel durations
-        rb = sum(alg_bytes(per_pose[p]) for p, _ in kms)
+        # roofline of the render kernel: algorithmic bytes of the frames timed / their kernel durations, against
+        # the HBM peak of ALL the GPUs the frame was split over
+        rb = sum(alg_bytes(per_pose[p]) for p in kposes)
         rt = float(kt.sum()) / 1e3
         achieved = rb / rt / 1e9
         traffic = ncu_traffic()
+        issue = ncu_issue()
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": bench_config(meta, args, world),
-            "ms_per_frame_by_pose": {str(p): float(np.mean([m for q, m in zip([k for k, _ in kms], kt) if q == p]))
+            "ms_per_frame_by_pose": {str(p): float(np.mean([m for q, m in zip(kposes, kt) if q == p]))
                                      for p in range(len(poses))},
+            "step_ms_by_pose": {str(p): float(np.mean([m for i, m in enumerate(step_ms) if i % len(poses) == p]))
+                                for p in range(len(poses))},
             "rays_per_frame_by_pose": [rays_of(c) for c in per_pose],
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+            "mrays_s_by_pose": {str(p): rays_of(per_pose[p]) / float(np.mean([m for i, m in enumerate(step_ms) if i % len(poses) == p])) / 1e3
+                                for p in range(len(poses))},
+            "frame_crc32": crc_info,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s",
+                         "frac": achieved / (peak * world), "peak_per_gpu": peak, "gpus": world,
+                         "traffic": (traffic["dram_bytes_per_launch"] if traffic and world == 1 else None),
+                         "traffic_source": ("profiles/traffic.json: ncu --set full capture of this kernel on this "
+                                            "workload (%s); not measured by this run" % traffic.get("source", "committed")
+                                            if traffic and world == 1 else None),
                          "peak_source": peak_src, "kernel": "render_fast_kernel" if kernel_used == 2 else "render_kernel",
                          "algorithmic_bytes_per_frame_by_pose": [alg_bytes(c) for c in per_pose],
-                         "kernel_ms_mean": float(kt.mean())},
+                         "kernel_ms_mean": float(kt.mean()),
+                         "note": "algorithmic bytes are 40-100x the DRAM traffic (L1 hit 94-98 %): HBM does not "
+                                 "bind this kernel, instruction issue does -- see roofline_issue"},
+            "roofline_issue": (dict(issue, source="profiles/issue_roofline.json (ncu capture of this kernel on this "
+                                                  "workload; not measured by this run)") if issue else None),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "wall_s_timed_region": wall, "kernel": {1: "generic", 2: "fast"}.get(kernel_used),
             "gather": args.gather if world > 1 else None,
             "division": {0: "glsl a*(1/b) (matches the reference shader on llvmpipe bit for bit)",
                          1: "ieee a/b (matches the reference CPU twin)"}[args.division],
         }
-        out["extras"] = {}
-        if c5 is not None:
-            out["extras"]["c5_64_views"] = c5
+        out["extras"] = extras
         if not args.no_c1 and world == 1:
             out["extras"]["c1_640x360"] = c1_gpu(K, local)
+            if not args.no_cpu:
+                # north_star's named baseline, next to the headline: the reference's UNMODIFIED shader on Mesa
+                # llvmpipe, on this box's host cores, same 640x360 frame as c1_640x360
+                out["extras"]["c1_640x360_reference_shader_on_llvmpipe"] = c1_llvmpipe()
         if not args.no_cpu and world == 1:
-            cores = os.cpu_count() or 1
+            cores = host_threads()
             rays, dt = 0, 0.0
             for rep in range(args.cpu_passes):
                 for p in range(len(poses)):
-                    a, b = cpu_port_sample(sc, poses[p], (0, HEIGHT), 0)
+                    a, b = cpu_port_sample(sc, poses[p], (0, HEIGHT), cores)
                     rays += a
                     dt += b
             out["cpu_baseline"] = {"value": rays / dt / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
                                    "sample": "oracle restatement of octree_fsh (both trees, shading): %d pass(es) over "
-                                             "the full 1080p frame of each of the %d poses, OpenMP over rows, "
-                                             "%.1f s of CPU wall time" % (args.cpu_passes, len(poses), dt)}
+                                             "the full frame of each of the %d poses, OpenMP over rows on %d threads, "
+                                             "%.1f s of CPU wall time" % (args.cpu_passes, len(poses), cores, dt)}
         emit(json.dumps(out))
 
-    sharded.close()
+    rig.unshard()
     barrier()
     rc.destroy()
     if world > 1:

@@ -11,6 +11,9 @@
  *   particle_glc_update()  particle_glc.c L118-156                                 -> octree_cuc_particles_update
  *   presentation           octree_glc.c L308-351                                   -> octree_cuc_enable_present
  *
+ * With --gpus N the same call sequence drives N GPUs (image tiles mod N, replicated octree, peer stores into the
+ * first GPU's framebuffer, device-side completion fence): nothing else in the host changes.
+ *
  * The scene is built with the host data model (qubatron_b200/host/qb_host.c,
  * the octree.c equivalent).  Links only against liboctree_cuc.so and libqb_host.so;
  * no CUDA headers are needed on the host side.  Prints the number of lit pixels
@@ -20,6 +23,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "../include/octree_cuc.h"
 
@@ -34,8 +38,20 @@ void       qb_octree_delete(qb_octree* t);
 #define GL_INT 0x1404
 #define GL_FLOAT 0x1406
 
-int main(void)
+/* host_demo [--gpus N] [--same-device]
+ *   --gpus N        drive N GPUs of the box from this one thread (octree_cuc_set_gpus): same calls, same frame
+ *   --same-device   put all N shards on GPU 0 (how a one-GPU box exercises the multi-GPU path) */
+int main(int argc, char** argv)
 {
+    int gpus = 1, same_device = 0;
+    for (int i = 1; i < argc; i++)
+    {
+        if (!strcmp(argv[i], "--gpus") && i + 1 < argc)
+            gpus = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--same-device"))
+            same_device = 1;
+    }
+
     /* modelutil.c L89-110 */
     float points[15]  = {10, 690, 10, 10, 340, 10, 10, 340, 690, 10, 10, 10, 690, 10, 690};
     float normals[15] = {0, 0, -1, 0, 0, -1, 0, 0, -1, 0, 0, -1, 0, 0, -1};
@@ -47,6 +63,14 @@ int main(void)
     qb_octree_insert_points(statoctr, points, 5, 0);
 
     octree_glc_t rc = octree_glc_init("shaders/"); /* qubatron.c L116 */
+    if (gpus > 1)
+    {
+        int devices[64] = {0}; /* all on the device init chose (0) when --same-device */
+        if (gpus > 64) return 3;
+        octree_cuc_set_gpus(&rc, gpus, same_device ? devices : NULL);
+        printf("driving %d GPU shard(s) from one thread%s\n", octree_cuc_gpu_count(&rc),
+               same_device ? " (all on GPU 0)" : "");
+    }
 
     /* modelutil.c L131-169 */
     octree_glc_upload_texbuffer_data(&rc, colors, GL_FLOAT, 5 * sizeof(float) * 3, sizeof(float) * 3, 0,

@@ -94,6 +94,21 @@ void octree_glc_upload_texbuffer_data(octree_glc_t* rc, void* data, int type, si
 
 /* ---- extensions ---------------------------------------------------------- */
 
+/* Multi-GPU from the engine's one thread (SURVEY 8b "choose GPU count"; the reference is one C thread making one
+ * call per frame, qubatron.c L116, L508-548).  Call right after octree_glc_init, before the first upload:
+ * the connector then drives n devices of the box from the calling thread.  devices = n device ordinals
+ * (devices[0] = the device octree_glc_init chose) or NULL for the next n - 1 devices after it.  From then on
+ *   - every upload, tree build, skinning pass and setting reaches all n devices (bulk ones on all devices at once),
+ *     so octree and point arrays are replicated;
+ *   - octree_glc_update / octree_cuc_update_views render image tiles `mod n`: every device's kernel stores its
+ *     tiles straight into the first device's framebuffer over NVLink (peer stores) and the last CTA of each
+ *     kernel publishes the frame number into the first device's fence words; no collective, no host round trip;
+ *   - read_frame / read_aux / read_window return the whole frame, counters are sums, last_frame_ms the slowest
+ *     device's kernel, last_step_ms the time until every device's tiles have arrived.
+ * The same ordinal may be given more than once (several shards on one GPU: how the single-GPU tests cover this). */
+void octree_cuc_set_gpus(octree_glc_t* rc, int n, const int* devices);
+int  octree_cuc_gpu_count(octree_glc_t* rc);
+
 /* choose the CUDA device used by the next octree_glc_init (default: current) */
 void octree_cuc_select_device(int device);
 
@@ -203,6 +218,11 @@ void octree_cuc_set_division(octree_glc_t* rc, int mode);
  * connector's stream); synchronises on the frame */
 float octree_cuc_last_frame_ms(octree_glc_t* rc);
 
+/* device time from the start of the last frame until it was complete: on the connector that collects a frame split
+ * over several (rank 0 of a fence, the primary of a group) this includes the wait for the other devices' tiles;
+ * elsewhere it equals octree_cuc_last_frame_ms */
+float octree_cuc_last_step_ms(octree_glc_t* rc);
+
 /* number of kernels this connector has launched since init */
 uint64_t octree_cuc_launch_count(octree_glc_t* rc);
 
@@ -227,8 +247,23 @@ void octree_cuc_reserve_frame(octree_glc_t* rc, int width, int height, int views
  * CUDA IPC handle, the other ranks open it and render their tiles straight
  * into it with peer stores (octree_cuc_set_frame_target). */
 void     octree_cuc_ipc_export_frame(octree_glc_t* rc, uint8_t* handle64);
+void     octree_cuc_ipc_export_ptr(octree_glc_t* rc, uint64_t device_ptr, uint8_t* handle64);
 uint64_t octree_cuc_ipc_open(octree_glc_t* rc, const uint8_t* handle64);
 void     octree_cuc_ipc_close(octree_glc_t* rc, uint64_t device_ptr);
+
+/* Completion fence for one frame split over several connectors -- one per process under torchrun, where
+ * octree_cuc_set_gpus cannot be used -- by device-side flags instead of a collective per frame.  Every connector owns
+ * a few fence words (octree_cuc_fence_device; export with octree_cuc_ipc_export_ptr, open with octree_cuc_ipc_open);
+ * octree_cuc_set_fence(rank, world, ptrs) takes the addresses of all `world` connectors' words as this device sees
+ * them (ptrs[rank] = its own).  Ranks > 0 render into rank 0's framebuffer (octree_cuc_set_frame_target); the last
+ * CTA of their kernel publishes the frame number to rank 0 (__threadfence_system + release store over NVLink), rank
+ * 0's stream waits for all of them in a one-warp kernel after its own tiles, and the first CTA of rank 0's NEXT
+ * frame tells the others that the previous frame has been consumed -- their pixel stores (not their traversal)
+ * wait for that.  Every rank must call octree_glc_update once per frame, rank 0 first when ranks share a device.
+ * A peer that never answers traps the waiting kernel after ~4 s instead of hanging the GPU.  world <= 1 or
+ * ptrs == NULL removes the fence. */
+uint64_t octree_cuc_fence_device(octree_glc_t* rc);
+void     octree_cuc_set_fence(octree_glc_t* rc, int rank, int world, const uint64_t* fence_ptrs);
 
 /* "Next" row: build an octree on the GPU from per-point octant paths, with the reference's
  * node numbering, straight into the traversal layout -- what the engine does on the CPU every frame with
@@ -344,9 +379,12 @@ void octree_cuc_unpin_host_buffer(octree_glc_t* rc, void* data);
  * for) since the last call of this function */
 double octree_cuc_take_upload_ms(octree_glc_t* rc);
 
-/* multi-GPU range updates: pending ranges can be exported as one packed blob
- * (header + payload) by the rank that received the host uploads, broadcast by
- * the caller (NCCL), and applied on every other rank. */
+/* multi-GPU range updates across processes: with the replication log enabled, EVERY range the connector receives
+ * through octree_glc_upload_texbuffer_data (batched or bulk, growth re-uploads included) is also recorded;
+ * octree_cuc_export_pending drains the log as one packed blob (header + descriptors + payload; call with NULL for
+ * the size), the caller broadcasts it (NCCL) and every other rank applies it.  apply_blob validates every
+ * descriptor before it touches anything. */
+void   octree_cuc_enable_replication_log(octree_glc_t* rc, int on);
 size_t octree_cuc_export_pending(octree_glc_t* rc, void* blob_host, size_t capacity);
 void   octree_cuc_apply_blob(octree_glc_t* rc, const void* blob_host, size_t bytes);
 

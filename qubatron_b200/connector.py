@@ -116,6 +116,13 @@ _PROTOS = {
     "octree_cuc_export_pending": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_void_p, C.c_size_t]),
     "octree_cuc_apply_blob": (None, [C.POINTER(octree_glc_t), C.c_void_p, C.c_size_t]),
     "octree_cuc_version": (C.c_char_p, []),
+    "octree_cuc_set_gpus": (None, [C.POINTER(octree_glc_t), C.c_int, C.c_void_p]),
+    "octree_cuc_gpu_count": (C.c_int, [C.POINTER(octree_glc_t)]),
+    "octree_cuc_last_step_ms": (C.c_float, [C.POINTER(octree_glc_t)]),
+    "octree_cuc_ipc_export_ptr": (None, [C.POINTER(octree_glc_t), C.c_uint64, C.c_void_p]),
+    "octree_cuc_fence_device": (C.c_uint64, [C.POINTER(octree_glc_t)]),
+    "octree_cuc_set_fence": (None, [C.POINTER(octree_glc_t), C.c_int, C.c_int, C.c_void_p]),
+    "octree_cuc_enable_replication_log": (None, [C.POINTER(octree_glc_t), C.c_int]),
 }
 
 _lib = None
@@ -306,6 +313,38 @@ class OctreeGlc:
         h = np.zeros(64, dtype=np.uint8)
         self.lib.octree_cuc_ipc_export_frame(self._p, h.ctypes.data_as(C.c_void_p))
         return h
+
+    def ipc_export_ptr(self, device_ptr):
+        h = np.zeros(64, dtype=np.uint8)
+        self.lib.octree_cuc_ipc_export_ptr(self._p, int(device_ptr), h.ctypes.data_as(C.c_void_p))
+        return h
+
+    def set_gpus(self, n, devices=None):
+        """octree_cuc_set_gpus: drive n devices from this one connector (call before the first upload)."""
+        if devices is None:
+            self.lib.octree_cuc_set_gpus(self._p, int(n), None)
+        else:
+            arr = (C.c_int * int(n))(*[int(d) for d in devices])
+            self.lib.octree_cuc_set_gpus(self._p, int(n), C.cast(arr, C.c_void_p))
+
+    def gpu_count(self):
+        return int(self.lib.octree_cuc_gpu_count(self._p))
+
+    def last_step_ms(self):
+        return float(self.lib.octree_cuc_last_step_ms(self._p))
+
+    def fence_device(self):
+        return int(self.lib.octree_cuc_fence_device(self._p))
+
+    def set_fence(self, rank, world, fence_ptrs):
+        if fence_ptrs is None:
+            self.lib.octree_cuc_set_fence(self._p, 0, 1, None)
+        else:
+            arr = (C.c_uint64 * int(world))(*[int(v) for v in fence_ptrs])
+            self.lib.octree_cuc_set_fence(self._p, int(rank), int(world), C.cast(arr, C.c_void_p))
+
+    def enable_replication_log(self, on=True):
+        self.lib.octree_cuc_enable_replication_log(self._p, int(bool(on)))
 
     def ipc_open(self, handle):
         h = np.ascontiguousarray(handle, dtype=np.uint8)

@@ -19,7 +19,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
+#include <thread>
 #include <vector>
 
 namespace
@@ -318,9 +320,65 @@ struct Impl
     uint64_t launches = 0;
     uint64_t memsize  = 0;
     double   upload_ms = 0.0; // host wall time spent in upload calls
+
+    // multi-GPU completion fence (octree_cuc_set_fence, FenceDev in octree_types.cuh)
+    unsigned*   fence_words     = nullptr; // FENCE_WORDS words on this device
+    unsigned**  fence_peers_dev = nullptr; // rank 0: device table of every rank's fence words
+    unsigned*   fence_peer0     = nullptr; // ranks != 0: rank 0's fence words as addressed from this device
+    unsigned*   fence_cta       = nullptr; // ranks != 0: finished-CTA counter of the running launch
+    int         fence_rank = 0, fence_n = 1;
+    unsigned    fence_seq  = 0;
+    cudaEvent_t ev_done    = nullptr; // rank 0: every rank's tiles of the last frame are in the framebuffer
+    // in-process multi-GPU group (octree_cuc_set_gpus): the connectors of the other devices, driven by the same calls
+    std::vector<octree_glc_t> replicas;
+    bool                      is_replica = false;
+    uint8_t*                  ext_flags  = nullptr; // replicas: the primary's parity planes
+    int*                      ext_aux    = nullptr;
+    // replication log (octree_cuc_enable_replication_log): every range this connector applied since the last export
+    bool                   repl_on = false;
+    std::vector<RangeDesc> repl_descs;
+    std::vector<char>      repl_payload;
 };
 
+// run `call` (which names the member connector `m`) on every connector of the group behind a primary
+#define REPLAY(I, call)                                                                                               \
+    do                                                                                                                \
+    {                                                                                                                 \
+        if (!(I)->replicas.empty())                                                                                   \
+        {                                                                                                             \
+            for (auto& r__ : (I)->replicas)                                                                           \
+            {                                                                                                         \
+                octree_glc_t* m = &r__;                                                                               \
+                call;                                                                                                 \
+            }                                                                                                         \
+            CUDA_OK(cudaSetDevice((I)->device));                                                                      \
+        }                                                                                                             \
+    } while (0)
+
 int g_selected_device = -1;
+
+// A heavy call (bulk upload, tree build, skinning) on every connector of a group AT THE SAME TIME: each device's
+// share runs on a thread of its own, because these calls wait for their device (count read-backs, staging reuse)
+// and N of them one after the other would take N times as long.  fn(member, is_primary).
+void run_on_group(octree_glc_t* rc, const std::function<void(octree_glc_t*, bool)>& fn)
+{
+    Impl* I = (Impl*) rc->impl;
+    if (I->replicas.empty())
+    {
+        fn(rc, true);
+        return;
+    }
+    std::vector<std::thread> th;
+    th.reserve(I->replicas.size());
+    for (auto& r : I->replicas)
+    {
+        octree_glc_t* m = &r;
+        th.emplace_back([&fn, m]() { fn(m, false); });
+    }
+    fn(rc, true);
+    for (auto& t : th) t.join();
+    CUDA_OK(cudaSetDevice(I->device));
+}
 
 Impl* impl_of(octree_glc_t* rc)
 {
@@ -456,15 +514,16 @@ void note_extent(Impl* I, int buftype, size_t end_byte)
     }
 }
 
-void upload_bulk(Impl* I, const char* data, int buftype, size_t s, size_t e)
+// `src` = the first byte of the range, i.e. logical byte s of the host array
+void upload_bulk(Impl* I, const char* src, int buftype, size_t s, size_t e)
 {
     flush_pending(I);
     const int t = tree_index(buftype);
     for (size_t off = s; off < e; off += STAGE_BYTES)
     {
         size_t n = e - off < STAGE_BYTES ? e - off : STAGE_BYTES;
-        // pageable source: the call returns once `data` has been consumed
-        CUDA_OK(cudaMemcpyAsync(I->stage_dev, data + off, n, cudaMemcpyHostToDevice, I->stream));
+        // pageable source: the call returns once the range has been consumed
+        CUDA_OK(cudaMemcpyAsync(I->stage_dev, src + (off - s), n, cudaMemcpyHostToDevice, I->stream));
         size_t   words  = n / 4;
         unsigned blocks = (unsigned) ((words + 255) / 256);
         if (is_octree(buftype) && off % 48 == 0 && n % 48 == 0)
@@ -489,7 +548,7 @@ void upload_bulk(Impl* I, const char* data, int buftype, size_t s, size_t e)
     CUDA_OK(cudaStreamSynchronize(I->stream));
 }
 
-void upload_batched(Impl* I, const char* data, int buftype, size_t s, size_t e)
+void upload_batched(Impl* I, const char* src, int buftype, size_t s, size_t e)
 {
     const size_t bytes = e - s;
     auto&        iv    = I->intervals[buftype];
@@ -499,7 +558,7 @@ void upload_batched(Impl* I, const char* data, int buftype, size_t s, size_t e)
     if (same != iv.end() && same->second.first == e)
     {
         const RangeDesc& d = I->descs[same->second.second];
-        memcpy(I->batch_host + (size_t) d.src_word * 4, data + s, bytes);
+        memcpy(I->batch_host + (size_t) d.src_word * 4, src, bytes);
         return;
     }
     // a different, overlapping pending range: apply what is queued first so that
@@ -520,10 +579,20 @@ void upload_batched(Impl* I, const char* data, int buftype, size_t s, size_t e)
     d.nwords   = (unsigned int) (bytes / 4);
     d.buftype  = buftype;
     d.pad      = 0;
-    memcpy(I->batch_host + I->batch_used, data + s, bytes);
+    memcpy(I->batch_host + I->batch_used, src, bytes);
     I->batch_used += bytes;
     I->intervals[buftype][s] = std::make_pair((unsigned long long) e, (int) I->descs.size());
     I->descs.push_back(d);
+}
+
+// one texel-granular range [s, e) of the logical array behind `buftype`; `src` = its first byte
+void apply_range(Impl* I, const char* src, int buftype, size_t s, size_t e)
+{
+    note_extent(I, buftype, e);
+    if (e - s <= SMALL_RANGE)
+        upload_batched(I, src, buftype, s, e);
+    else
+        upload_bulk(I, src, buftype, s, e);
 }
 
 // The kernels clamp every node index to device node `nodes + 1`, which must read as an empty node.  Memory behind
@@ -716,6 +785,50 @@ void launch_fast(Impl* I, const FrameParams& P, unsigned blocks)
         dyn ? launch_fast_dyn<DIV_IEEE, true>(I, P, blocks) : launch_fast_dyn<DIV_IEEE, false>(I, P, blocks);
 }
 
+// octree_glc.c L268-269, L288: render size from the window size and the quality setting
+void render_size(float width, float height, uint8_t quality, float& ow, float& oh, int& W, int& H)
+{
+    ow = (float) ((double) width / (6.0 - (double) (float) quality / 2.0));
+    oh = (float) ((double) height / (6.0 - (double) (float) quality / 2.0));
+    W  = (int) ow;
+    H  = (int) oh;
+}
+
+// the connector's own framebuffer / parity planes for `total` pixels (all views of a batch)
+void ensure_frame(Impl* I, size_t total)
+{
+    if (total <= I->frame_cap) return;
+    if (I->frame)
+    {
+        CUDA_OK(cudaStreamSynchronize(I->stream));
+        if (I->copy_stream) CUDA_OK(cudaStreamSynchronize(I->copy_stream));
+        CUDA_OK(cudaFree(I->frame));
+        I->memsize -= I->frame_cap * 4;
+    }
+    CUDA_OK(cudaMalloc(&I->frame, total * 4));
+    CUDA_OK(cudaMemsetAsync(I->frame, 0, total * 4, I->stream));
+    I->frame_cap = total;
+    I->memsize += I->frame_cap * 4;
+}
+void ensure_aux(Impl* I, size_t total)
+{
+    if (total <= I->aux_cap) return;
+    if (I->flags)
+    {
+        CUDA_OK(cudaStreamSynchronize(I->stream));
+        CUDA_OK(cudaFree(I->flags));
+        CUDA_OK(cudaFree(I->aux));
+        I->memsize -= I->aux_cap * 25;
+    }
+    CUDA_OK(cudaMalloc(&I->flags, total));
+    CUDA_OK(cudaMalloc(&I->aux, total * 6 * sizeof(int)));
+    // tiles of other ranks stay untouched: they must not read as garbage
+    CUDA_OK(cudaMemsetAsync(I->flags, 0, total, I->stream));
+    CUDA_OK(cudaMemsetAsync(I->aux, 0, total * 6 * sizeof(int), I->stream));
+    I->aux_cap = total;
+    I->memsize += I->aux_cap * 25;
+}
+
 void render_views(octree_glc_t* rc, int n, float width, float height, const float* positions, const float* angles,
                   float lighta, uint8_t quality, int maxlevel, float basesize, int shoot)
 {
@@ -724,41 +837,15 @@ void render_views(octree_glc_t* rc, int n, float width, float height, const floa
     if (maxlevel < 0 || maxlevel > GENERIC_STACK - 1) die("maxlevel out of range (reference stack is 18 levels)");
     flush_pending(I);
 
-    // octree_glc.c L268-269, L288
-    const float ow = (float) ((double) width / (6.0 - (double) (float) quality / 2.0));
-    const float oh = (float) ((double) height / (6.0 - (double) (float) quality / 2.0));
-    const int   W = (int) ow, H = (int) oh;
+    float ow, oh;
+    int   W, H;
+    render_size(width, height, quality, ow, oh, W, H);
     if (W <= 0 || H <= 0) return;
     const size_t pixels = (size_t) W * H;
+    const bool   fenced = I->fence_n > 1;
 
-    if (!I->ext_target && pixels * n > I->frame_cap)
-    {
-        if (I->frame)
-        {
-            CUDA_OK(cudaStreamSynchronize(I->stream));
-            if (I->ring_on) CUDA_OK(cudaStreamSynchronize(I->copy_stream));
-            CUDA_OK(cudaFree(I->frame));
-            I->memsize -= I->frame_cap * 4;
-        }
-        CUDA_OK(cudaMalloc(&I->frame, pixels * n * 4));
-        CUDA_OK(cudaMemsetAsync(I->frame, 0, pixels * n * 4, I->stream));
-        I->frame_cap = pixels * n;
-        I->memsize += I->frame_cap * 4;
-    }
-    if (I->aux_on && pixels * n > I->aux_cap)
-    {
-        if (I->flags)
-        {
-            CUDA_OK(cudaStreamSynchronize(I->stream));
-            CUDA_OK(cudaFree(I->flags));
-            CUDA_OK(cudaFree(I->aux));
-            I->memsize -= I->aux_cap * 25;
-        }
-        CUDA_OK(cudaMalloc(&I->flags, pixels * n));
-        CUDA_OK(cudaMalloc(&I->aux, pixels * n * 6 * sizeof(int)));
-        I->aux_cap = pixels * n;
-        I->memsize += I->aux_cap * 25;
-    }
+    if (!I->ext_target) ensure_frame(I, pixels * n);
+    if (I->aux_on && !I->ext_aux) ensure_aux(I, pixels * n);
     if (n > I->views_cap)
     {
         if (I->views_host)
@@ -819,7 +906,7 @@ void render_views(octree_glc_t* rc, int n, float width, float height, const floa
     }
     else
     {
-        if (I->ring_on)
+        if (I->ring_on && !fenced)
         {
             I->ring_cur ^= 1;
             if (I->ring_cur == 1 && pixels * n > I->frame_alt_cap)
@@ -831,19 +918,35 @@ void render_views(octree_glc_t* rc, int n, float width, float height, const floa
                     I->memsize -= I->frame_alt_cap * 4;
                 }
                 CUDA_OK(cudaMalloc(&I->frame_alt, pixels * n * 4));
+                CUDA_OK(cudaMemsetAsync(I->frame_alt, 0, pixels * n * 4, I->stream)); // tiles of other ranks
                 I->frame_alt_cap = pixels * n;
                 I->memsize += I->frame_alt_cap * 4;
             }
             // the copy that last read this buffer must be done before the kernel overwrites it
             if (I->copy_pending[I->ring_cur]) CUDA_OK(cudaStreamWaitEvent(I->stream, I->ev_copy[I->ring_cur], 0));
         }
-        P.frame       = (I->ring_on && I->ring_cur == 1) ? I->frame_alt : I->frame;
+        P.frame       = (I->ring_on && !fenced && I->ring_cur == 1) ? I->frame_alt : I->frame;
         P.pitch       = W;
         P.view_stride = pixels;
     }
-    P.flags    = I->flags;
-    P.aux      = I->aux;
+    P.flags    = I->ext_aux ? I->ext_flags : I->flags;
+    P.aux      = I->ext_aux ? I->ext_aux : I->aux;
     P.counters = I->counters;
+    if (fenced)
+    {
+        // completion fence of a frame split over several connectors (FenceDev, octree_types.cuh)
+        P.fence.seq = ++I->fence_seq;
+        P.fence.n   = I->fence_n;
+        if (I->fence_rank == 0)
+            P.fence.peers = I->fence_peers_dev;
+        else
+        {
+            if (!I->ext_target) die("update: a fenced connector of rank > 0 renders into rank 0's frame (set_frame_target)");
+            P.fence.done      = I->fence_peer0 + I->fence_rank;
+            P.fence.gate      = I->fence_words + FENCE_CONSUMED;
+            P.fence.cta_count = I->fence_cta;
+        }
+    }
 
     P.tile_w            = I->tile_w;
     P.tile_h            = I->tile_h;
@@ -954,8 +1057,24 @@ void render_views(octree_glc_t* rc, int n, float width, float height, const floa
         I->launches++;
         I->last_kernel = fast ? 2 : 1;
     }
+    else if (fenced)
+    {
+        // no tile of this frame here: the fence signals still have to go out
+        fence_signal_kernel<<<1, 64, 0, I->stream>>>(P.fence);
+        CUDA_OK(cudaGetLastError());
+        I->launches++;
+    }
     if (!ev1_recorded) CUDA_OK(cudaEventRecord(I->ev1, I->stream));
-    if (I->present_on && n == 1 && I->shard_world == 1) // octree_glc.c L308-351; after ev1: not part of the frame time
+    if (fenced && I->fence_rank == 0)
+    {
+        // the frame is complete once every rank has published its number (peer stores + release, no collective)
+        fence_wait_done_kernel<<<1, 64, 0, I->stream>>>(I->fence_words, I->fence_n, P.fence.seq);
+        CUDA_OK(cudaGetLastError());
+        I->launches++;
+        CUDA_OK(cudaEventRecord(I->ev_done, I->stream));
+    }
+    // octree_glc.c L308-351; after ev1: not part of the frame time
+    if (I->present_on && n == 1 && (I->shard_world == 1 || (fenced && I->fence_rank == 0)))
     {
         const int ww = (int) width, wh = (int) height;
         if (ww > 0 && wh > 0)
@@ -990,9 +1109,87 @@ void render_views(octree_glc_t* rc, int n, float width, float height, const floa
             I->window_h = wh;
         }
     }
-    if (I->ring_on && !I->ext_target) CUDA_OK(cudaEventRecord(I->ev_render[I->ring_cur], I->stream));
+    if (I->ring_on && !fenced && !I->ext_target) CUDA_OK(cudaEventRecord(I->ev_render[I->ring_cur], I->stream));
     I->timed = true;
     publish_memsize(rc, I);
+}
+
+// One frame (or batch of views) on every device of an in-process group: the primary's framebuffer is the target of
+// all of them, each connector renders its tiles (octree_cuc_set_gpus has set the shards) and the device-side fence
+// completes the frame on the primary's stream.
+void group_render(octree_glc_t* rc, int n, float width, float height, const float* positions, const float* angles,
+                  float lighta, uint8_t quality, int maxlevel, float basesize, int shoot)
+{
+    Impl* I = impl_of(rc);
+    if (I->replicas.empty())
+    {
+        render_views(rc, n, width, height, positions, angles, lighta, quality, maxlevel, basesize, shoot);
+        return;
+    }
+    if (n <= 0) return;
+    float ow, oh;
+    int   W, H;
+    render_size(width, height, quality, ow, oh, W, H);
+    if (W <= 0 || H <= 0) return;
+    if (I->ext_target) die("update: an external frame target cannot be combined with octree_cuc_set_gpus");
+    const size_t total = (size_t) W * H * n;
+    ensure_frame(I, total);
+    if (I->aux_on) ensure_aux(I, total);
+    for (auto& r : I->replicas)
+    {
+        Impl* R       = (Impl*) r.impl;
+        R->ext_target = (uint64_t) (uintptr_t) I->frame;
+        R->ext_pitch  = (size_t) W;
+        R->ext_flags  = I->aux_on ? I->flags : nullptr;
+        R->ext_aux    = I->aux_on ? I->aux : nullptr;
+    }
+    // the primary first: its kernel carries the "previous frame consumed" signal the others' stores wait for
+    render_views(rc, n, width, height, positions, angles, lighta, quality, maxlevel, basesize, shoot);
+    REPLAY(I, render_views(m, n, width, height, positions, angles, lighta, quality, maxlevel, basesize, shoot));
+    // device memory of the whole group
+    uint64_t mem = I->memsize;
+    for (auto& r : I->replicas) mem += ((Impl*) r.impl)->memsize;
+    rc->memsize_bytes = mem;
+    rc->memsize       = mem > 0xffffffffull ? 0xffffffffu : (unsigned int) mem;
+}
+
+unsigned* fence_alloc(Impl* I)
+{
+    if (!I->fence_words)
+    {
+        CUDA_OK(cudaMalloc(&I->fence_words, FENCE_WORDS * sizeof(unsigned)));
+        CUDA_OK(cudaMemset(I->fence_words, 0, FENCE_WORDS * sizeof(unsigned)));
+        CUDA_OK(cudaMalloc(&I->fence_cta, sizeof(unsigned)));
+        CUDA_OK(cudaMemset(I->fence_cta, 0, sizeof(unsigned)));
+        CUDA_OK(cudaMalloc(&I->fence_peers_dev, 64 * sizeof(unsigned*)));
+        CUDA_OK(cudaMemset(I->fence_peers_dev, 0, 64 * sizeof(unsigned*)));
+        CUDA_OK(cudaEventCreate(&I->ev_done));
+    }
+    return I->fence_words;
+}
+
+void fence_wire(Impl* I, int rank, int world, const uint64_t* ptrs)
+{
+    CUDA_OK(cudaSetDevice(I->device));
+    flush_pending(I);
+    CUDA_OK(cudaStreamSynchronize(I->stream));
+    if (world <= 1 || ptrs == nullptr)
+    {
+        I->fence_rank = 0, I->fence_n = 1, I->fence_seq = 0;
+        return;
+    }
+    if (world > 64 || rank < 0 || rank >= world) die("set_fence: need 0 <= rank < world <= 64");
+    fence_alloc(I);
+    if ((uint64_t) (uintptr_t) I->fence_words != ptrs[rank]) die("set_fence: entry `rank` must be this connector's own fence words");
+    CUDA_OK(cudaMemset(I->fence_words, 0, FENCE_WORDS * sizeof(unsigned)));
+    CUDA_OK(cudaMemset(I->fence_cta, 0, sizeof(unsigned)));
+    unsigned* table[64] = {};
+    for (int k = 0; k < world; k++) table[k] = (unsigned*) (uintptr_t) ptrs[k];
+    CUDA_OK(cudaMemcpy(I->fence_peers_dev, table, sizeof(table), cudaMemcpyHostToDevice));
+    I->fence_peer0 = table[0];
+    I->fence_rank  = rank;
+    I->fence_n     = world;
+    I->fence_seq   = 0;
 }
 
 } // namespace
@@ -1066,6 +1263,16 @@ void octree_cuc_destroy(octree_glc_t* rc)
     if (!rc || !rc->impl) return;
     Impl* I = impl_of(rc);
     CUDA_OK(cudaStreamSynchronize(I->stream));
+    for (auto& r : I->replicas) octree_cuc_destroy(&r);
+    I->replicas.clear();
+    CUDA_OK(cudaSetDevice(I->device));
+    if (I->fence_words)
+    {
+        cudaFree(I->fence_words);
+        cudaFree(I->fence_cta);
+        cudaFree(I->fence_peers_dev);
+        cudaEventDestroy(I->ev_done);
+    }
     for (int t = 0; t < 2; t++)
     {
         dev_free(I, I->tree[t].child);
@@ -1122,8 +1329,11 @@ void octree_cuc_destroy(octree_glc_t* rc)
     rc->memsize_bytes = 0;
 }
 
-void octree_glc_upload_texbuffer_data(octree_glc_t* rc, void* data, int type, size_t size, size_t itemsize,
-                                      size_t start, size_t end, octree_glc_buffer_t buftype)
+} // extern "C"
+namespace
+{
+void upload_one(octree_glc_t* rc, void* data, int type, size_t size, size_t itemsize, size_t start, size_t end,
+                octree_glc_buffer_t buftype)
 {
     Impl* I = impl_of(rc);
     struct Timer
@@ -1151,13 +1361,50 @@ void octree_glc_upload_texbuffer_data(octree_glc_t* rc, void* data, int type, si
     if (e > (size / itemsize) * itemsize) e = (size / itemsize) * itemsize;
     if (e > s)
     {
-        note_extent(I, buftype, e);
-        if (e - s <= SMALL_RANGE)
-            upload_batched(I, (const char*) data, buftype, s, e);
-        else
-            upload_bulk(I, (const char*) data, buftype, s, e);
+        apply_range(I, (const char*) data + s, buftype, s, e);
+        if (I->repl_on) // for the connectors of other processes (octree_cuc_export_pending)
+        {
+            RangeDesc d;
+            d.dst_word = s / 4;
+            d.src_word = (unsigned int) (I->repl_payload.size() / 4);
+            d.nwords   = (unsigned int) ((e - s) / 4);
+            d.buftype  = buftype;
+            d.pad      = 0;
+            if (I->repl_payload.size() + (e - s) >= ((size_t) 1 << 34)) die("replication log exceeds 16 GiB: export it");
+            I->repl_descs.push_back(d);
+            I->repl_payload.insert(I->repl_payload.end(), (const char*) data + s, (const char*) data + e);
+        }
     }
     publish_memsize(rc, I);
+}
+} // namespace
+extern "C" {
+
+void octree_glc_upload_texbuffer_data(octree_glc_t* rc, void* data, int type, size_t size, size_t itemsize,
+                                      size_t start, size_t end, octree_glc_buffer_t buftype)
+{
+    Impl* I = impl_of(rc);
+    if (I->replicas.empty())
+    {
+        upload_one(rc, data, type, size, itemsize, start, end, buftype);
+        return;
+    }
+    // every device of the group takes the same call (same state, so the same growth decisions).  The thousands of
+    // 48-byte range uploads of a shot are a memcpy into pinned staging each: one after the other; a bulk range or a
+    // growing array waits for its device: all devices at once.
+    bool heavy = end > start && end - start > SMALL_RANGE;
+    if ((int) buftype >= 0 && (int) buftype <= 5)
+    {
+        const int t = tree_index(buftype);
+        heavy = heavy || (is_octree(buftype) ? (size + 47) / 48 > I->tree[t].cap_nodes : (size + 11) / 12 > I->pts[t].cap_points);
+    }
+    if (heavy)
+        run_on_group(rc, [=](octree_glc_t* m, bool) { upload_one(m, data, type, size, itemsize, start, end, buftype); });
+    else
+    {
+        upload_one(rc, data, type, size, itemsize, start, end, buftype);
+        REPLAY(I, upload_one(m, data, type, size, itemsize, start, end, buftype));
+    }
 }
 
 void octree_glc_update(octree_glc_t* rc, float width, float height, v3_t position, v3_t angle, float lighta,
@@ -1165,20 +1412,21 @@ void octree_glc_update(octree_glc_t* rc, float width, float height, v3_t positio
 {
     const float pos[3] = {position.x, position.y, position.z};
     const float ang[3] = {angle.x, angle.y, angle.z};
-    render_views(rc, 1, width, height, pos, ang, lighta, quality, maxlevel, basesize, shoot);
+    group_render(rc, 1, width, height, pos, ang, lighta, quality, maxlevel, basesize, shoot);
 }
 
 void octree_cuc_update_views(octree_glc_t* rc, int n, float width, float height, const float* positions,
                              const float* angles, float lighta, uint8_t quality, int maxlevel, float basesize,
                              int shoot)
 {
-    render_views(rc, n, width, height, positions, angles, lighta, quality, maxlevel, basesize, shoot);
+    group_render(rc, n, width, height, positions, angles, lighta, quality, maxlevel, basesize, shoot);
 }
 
 void octree_cuc_sync(octree_glc_t* rc)
 {
     Impl* I = impl_of(rc);
     flush_pending(I);
+    REPLAY(I, octree_cuc_sync(m)); // the primary's stream waits for the others' frames: they finish first
     CUDA_OK(cudaStreamSynchronize(I->stream));
 }
 
@@ -1203,7 +1451,12 @@ size_t octree_cuc_read_frame(octree_glc_t* rc, uint8_t* rgba_host, size_t capaci
 
 void octree_cuc_enable_present(octree_glc_t* rc, int on) { impl_of(rc)->present_on = on != 0; }
 
-void octree_cuc_set_tile_feedback(octree_glc_t* rc, int on) { impl_of(rc)->feedback_on = on != 0; }
+void octree_cuc_set_tile_feedback(octree_glc_t* rc, int on)
+{
+    Impl* I        = impl_of(rc);
+    I->feedback_on = on != 0;
+    REPLAY(I, octree_cuc_set_tile_feedback(m, on));
+}
 
 size_t octree_cuc_read_window(octree_glc_t* rc, uint8_t* rgba_host, size_t capacity, int* width, int* height)
 {
@@ -1232,6 +1485,8 @@ size_t octree_cuc_read_frame_async(octree_glc_t* rc, uint8_t* rgba_host, size_t 
     size_t bytes = (size_t) I->W * I->H * 4 * (I->n_views ? I->n_views : 1);
     if (I->ext_target) die("read_frame_async: frame target is external, read it there");
     if (bytes == 0 || capacity < bytes) return 0;
+    // a frame other connectors store into stays where it is: snapshot, then copy (octree_cuc_read_frame_staged)
+    if (I->fence_n > 1) return octree_cuc_read_frame_staged(rc, rgba_host, capacity);
     if (!I->ring_on)
     {
         // first use: from now on frames alternate between two buffers; the frame just rendered is in `frame`
@@ -1312,7 +1567,12 @@ void octree_cuc_set_frame_target(octree_glc_t* rc, uint64_t device_ptr, size_t p
     I->ext_pitch  = pitch_pixels;
 }
 
-void octree_cuc_enable_aux(octree_glc_t* rc, int enable) { impl_of(rc)->aux_on = enable != 0; }
+void octree_cuc_enable_aux(octree_glc_t* rc, int enable)
+{
+    Impl* I   = impl_of(rc);
+    I->aux_on = enable != 0;
+    REPLAY(I, octree_cuc_enable_aux(m, enable));
+}
 
 size_t octree_cuc_read_aux(octree_glc_t* rc, uint8_t* flags_host, int32_t* aux_host)
 {
@@ -1326,7 +1586,12 @@ size_t octree_cuc_read_aux(octree_glc_t* rc, uint8_t* flags_host, int32_t* aux_h
     return pixels;
 }
 
-void octree_cuc_enable_counters(octree_glc_t* rc, int enable) { impl_of(rc)->count_on = enable != 0; }
+void octree_cuc_enable_counters(octree_glc_t* rc, int enable)
+{
+    Impl* I     = impl_of(rc);
+    I->count_on = enable != 0;
+    REPLAY(I, octree_cuc_enable_counters(m, enable));
+}
 
 void octree_cuc_read_counters(octree_glc_t* rc, octree_cuc_counters* out)
 {
@@ -1344,11 +1609,21 @@ void octree_cuc_read_counters(octree_glc_t* rc, octree_cuc_counters* out)
     out->hits         = (int64_t) h[CNT_HITS];
     out->discards     = (int64_t) h[CNT_DISCARDS];
     out->descents     = (int64_t) h[CNT_DESCENTS];
+    for (auto& r : I->replicas) // a group's counters are the sums over its devices
+    {
+        octree_cuc_counters c;
+        octree_cuc_read_counters(&r, &c);
+        int64_t*       a = &out->rays_primary;
+        const int64_t* b = &c.rays_primary;
+        for (int i = 0; i < CNT_COUNT; i++) a[i] += b[i];
+    }
+    if (!I->replicas.empty()) CUDA_OK(cudaSetDevice(I->device));
 }
 
 void octree_cuc_set_shard(octree_glc_t* rc, int rank, int world, int tile_w, int tile_h)
 {
     Impl* I = impl_of(rc);
+    if (!I->replicas.empty()) die("set_shard: the shards of an octree_cuc_set_gpus group are managed by the connector");
     if (world < 1 || rank < 0 || rank >= world) die("set_shard: need 0 <= rank < world");
     if (tile_w <= 0 || tile_h <= 0 || tile_w % BLOCK_W || tile_h % BLOCK_H)
         die("set_shard: tile size must be a multiple of 16 x 8 pixels");
@@ -1363,12 +1638,15 @@ void octree_cuc_set_light(octree_glc_t* rc, const float* light)
     Impl* I           = impl_of(rc);
     I->light_override = light != nullptr;
     if (light) memcpy(I->light, light, sizeof(I->light));
+    REPLAY(I, octree_cuc_set_light(m, light));
 }
 
 void octree_cuc_set_kernel(octree_glc_t* rc, int which)
 {
     if (which < 0 || which > 2) die("set_kernel: 0 auto, 1 generic, 2 fast");
-    impl_of(rc)->kernel_choice = which;
+    Impl* I          = impl_of(rc);
+    I->kernel_choice = which;
+    REPLAY(I, octree_cuc_set_kernel(m, which));
 }
 
 int octree_cuc_last_kernel(octree_glc_t* rc) { return impl_of(rc)->last_kernel; }
@@ -1376,7 +1654,9 @@ int octree_cuc_last_kernel(octree_glc_t* rc) { return impl_of(rc)->last_kernel; 
 void octree_cuc_set_division(octree_glc_t* rc, int mode)
 {
     if (mode != DIV_GLSL && mode != DIV_IEEE) die("set_division: 0 = GLSL a*(1/b), 1 = IEEE a/b");
-    impl_of(rc)->div_mode = mode;
+    Impl* I     = impl_of(rc);
+    I->div_mode = mode;
+    REPLAY(I, octree_cuc_set_division(m, mode));
 }
 
 float octree_cuc_last_frame_ms(octree_glc_t* rc)
@@ -1386,10 +1666,33 @@ float octree_cuc_last_frame_ms(octree_glc_t* rc)
     CUDA_OK(cudaEventSynchronize(I->ev1));
     float ms = 0.0f;
     CUDA_OK(cudaEventElapsedTime(&ms, I->ev0, I->ev1));
+    for (auto& r : I->replicas) // a group's kernel time is its slowest device's
+    {
+        const float v = octree_cuc_last_frame_ms(&r);
+        if (v > ms) ms = v;
+    }
+    if (!I->replicas.empty()) CUDA_OK(cudaSetDevice(I->device));
     return ms;
 }
 
-uint64_t octree_cuc_launch_count(octree_glc_t* rc) { return impl_of(rc)->launches; }
+float octree_cuc_last_step_ms(octree_glc_t* rc)
+{
+    Impl* I = impl_of(rc);
+    if (!I->timed) return 0.0f;
+    if (!(I->fence_n > 1 && I->fence_rank == 0)) return octree_cuc_last_frame_ms(rc);
+    CUDA_OK(cudaEventSynchronize(I->ev_done));
+    float ms = 0.0f;
+    CUDA_OK(cudaEventElapsedTime(&ms, I->ev0, I->ev_done));
+    return ms;
+}
+
+uint64_t octree_cuc_launch_count(octree_glc_t* rc)
+{
+    Impl*    I = impl_of(rc);
+    uint64_t n = I->launches;
+    for (auto& r : I->replicas) n += ((Impl*) r.impl)->launches;
+    return n;
+}
 
 void octree_cuc_set_stream(octree_glc_t* rc, uint64_t cuda_stream)
 {
@@ -1403,18 +1706,8 @@ void octree_cuc_reserve_frame(octree_glc_t* rc, int width, int height, int views
 {
     Impl*  I      = impl_of(rc);
     size_t pixels = (size_t) width * height * (views > 0 ? views : 1);
-    if (pixels <= I->frame_cap) return;
+    ensure_frame(I, pixels);
     CUDA_OK(cudaStreamSynchronize(I->stream));
-    if (I->frame)
-    {
-        CUDA_OK(cudaFree(I->frame));
-        I->memsize -= I->frame_cap * 4;
-    }
-    CUDA_OK(cudaMalloc(&I->frame, pixels * 4));
-    CUDA_OK(cudaMemsetAsync(I->frame, 0, pixels * 4, I->stream));
-    CUDA_OK(cudaStreamSynchronize(I->stream));
-    I->frame_cap = pixels;
-    I->memsize += pixels * 4;
     publish_memsize(rc, I);
 }
 
@@ -1446,10 +1739,93 @@ void octree_cuc_ipc_close(octree_glc_t* rc, uint64_t device_ptr)
     CUDA_OK(cudaIpcCloseMemHandle((void*) (uintptr_t) device_ptr));
 }
 
+void octree_cuc_ipc_export_ptr(octree_glc_t* rc, uint64_t device_ptr, uint8_t* handle64)
+{
+    impl_of(rc);
+    cudaIpcMemHandle_t h;
+    CUDA_OK(cudaIpcGetMemHandle(&h, (void*) (uintptr_t) device_ptr));
+    memcpy(handle64, &h, 64);
+}
+
+uint64_t octree_cuc_fence_device(octree_glc_t* rc) { return (uint64_t) (uintptr_t) fence_alloc(impl_of(rc)); }
+
+void octree_cuc_set_fence(octree_glc_t* rc, int rank, int world, const uint64_t* fence_ptrs)
+{
+    Impl* I = impl_of(rc);
+    if (!I->replicas.empty() || I->is_replica) die("set_fence: the fence of an octree_cuc_set_gpus group is managed by the connector");
+    fence_wire(I, rank, world, fence_ptrs);
+}
+
+int octree_cuc_gpu_count(octree_glc_t* rc) { return 1 + (int) impl_of(rc)->replicas.size(); }
+
+void octree_cuc_set_gpus(octree_glc_t* rc, int n, const int* devices)
+{
+    Impl* I = impl_of(rc);
+    if (I->is_replica) die("set_gpus: not on a member of a group");
+    if (!I->replicas.empty() || I->fence_n > 1) die("set_gpus: the group is already set up");
+    if (n < 1 || n > 64) die("set_gpus: 1 <= n <= 64");
+    for (int t = 0; t < 2; t++)
+        if (I->tree[t].nodes || I->pts[t].points || !I->descs.empty())
+            die("set_gpus: call it right after octree_glc_init, before the first upload");
+    if (n == 1) return;
+    int ndev = 0;
+    CUDA_OK(cudaGetDeviceCount(&ndev));
+    if (devices && devices[0] != I->device) die("set_gpus: devices[0] must be the device octree_glc_init chose");
+    if (!devices && n > ndev) die("set_gpus: more GPUs asked for than the box has");
+    uint64_t words[64];
+    words[0] = (uint64_t) (uintptr_t) fence_alloc(I);
+    const int saved = g_selected_device;
+    for (int k = 1; k < n; k++)
+    {
+        const int dev = devices ? devices[k] : (I->device + k) % ndev;
+        if (dev < 0 || dev >= ndev) die("set_gpus: no such device");
+        if (dev != I->device)
+        {
+            // the render kernels of device `dev` store into the primary's framebuffer and fence words, and the
+            // primary's kernel into theirs
+            int can = 0;
+            CUDA_OK(cudaDeviceCanAccessPeer(&can, dev, I->device));
+            if (!can) die("set_gpus: the devices cannot access each other's memory (no NVLink / PCIe peer path)");
+            for (int dir = 0; dir < 2; dir++)
+            {
+                CUDA_OK(cudaSetDevice(dir ? I->device : dev));
+                cudaError_t e = cudaDeviceEnablePeerAccess(dir ? dev : I->device, 0);
+                if (e == cudaErrorPeerAccessAlreadyEnabled)
+                    (void) cudaGetLastError();
+                else
+                    CUDA_OK(e);
+            }
+        }
+        g_selected_device = dev;
+        octree_glc_t r    = octree_glc_init(nullptr);
+        Impl*        R    = (Impl*) r.impl;
+        R->is_replica     = true;
+        R->div_mode       = I->div_mode;
+        R->kernel_choice  = I->kernel_choice;
+        R->feedback_on    = I->feedback_on;
+        R->aux_on         = I->aux_on;
+        R->count_on       = I->count_on;
+        R->light_override = I->light_override;
+        memcpy(R->light, I->light, sizeof(I->light));
+        words[k] = (uint64_t) (uintptr_t) fence_alloc(R);
+        I->replicas.push_back(r);
+    }
+    g_selected_device = saved;
+    // image tiles `mod n`, all stored into the primary's framebuffer, completed by the device-side fence
+    for (int k = 0; k < n; k++)
+    {
+        Impl* M        = k ? (Impl*) I->replicas[k - 1].impl : I;
+        M->shard_rank  = k;
+        M->shard_world = n;
+        fence_wire(M, k, n, words);
+    }
+    CUDA_OK(cudaSetDevice(I->device));
+}
+
 void octree_cuc_pin_host_buffer(octree_glc_t* rc, void* data, size_t bytes)
 {
     impl_of(rc);
-    CUDA_OK(cudaHostRegister(data, bytes, cudaHostRegisterDefault));
+    CUDA_OK(cudaHostRegister(data, bytes, cudaHostRegisterPortable)); // page-locked for every device of a group
 }
 
 void octree_cuc_unpin_host_buffer(octree_glc_t* rc, void* data)
@@ -1618,9 +1994,11 @@ size_t build_from_device_paths(Impl* I, int buftype, const int* p14, const int* 
 
 extern "C" {
 
-size_t octree_cuc_build_octree_from_paths(octree_glc_t* rc, const int32_t* oct14, const int32_t* oct54,
-                                          const int32_t* oct94, size_t n, int first_modind, int paths_on_device,
-                                          octree_glc_buffer_t buftype)
+} // extern "C"
+namespace
+{
+size_t build_octree_one(octree_glc_t* rc, const int32_t* oct14, const int32_t* oct54, const int32_t* oct94, size_t n,
+                        int first_modind, int paths_on_device, octree_glc_buffer_t buftype)
 {
     Impl* I = impl_of(rc);
     if (!is_octree(buftype)) die("build_octree_from_paths: buftype must be an octree buffer");
@@ -1645,9 +2023,8 @@ size_t octree_cuc_build_octree_from_paths(octree_glc_t* rc, const int32_t* oct14
     return total;
 }
 
-size_t octree_cuc_voxelise_and_build(octree_glc_t* rc, const float* pos, const uint8_t* col_u8, const float* nrm,
-                                     size_t n, int size, int levels, int inputs_on_device, int dynamic,
-                                     int64_t* order_host, float* pos_host)
+size_t voxelise_one(octree_glc_t* rc, const float* pos, const uint8_t* col_u8, const float* nrm, size_t n, int size,
+                    int levels, int inputs_on_device, int dynamic, int64_t* order_host, float* pos_host)
 {
     Impl* I = impl_of(rc);
     if (levels < 1 || levels > 12) die("voxelise_and_build: 1 <= levels <= 12");
@@ -1732,6 +2109,40 @@ size_t octree_cuc_voxelise_and_build(octree_glc_t* rc, const float* pos, const u
     publish_memsize(rc, I);
     return m;
 }
+} // namespace
+
+extern "C" {
+
+size_t octree_cuc_build_octree_from_paths(octree_glc_t* rc, const int32_t* oct14, const int32_t* oct54,
+                                          const int32_t* oct94, size_t n, int first_modind, int paths_on_device,
+                                          octree_glc_buffer_t buftype)
+{
+    Impl* I = impl_of(rc);
+    if (paths_on_device && !I->replicas.empty())
+        die("build_octree_from_paths: device-resident paths belong to one GPU; a multi-GPU group takes host paths");
+    size_t total = 0;
+    run_on_group(rc, [&](octree_glc_t* m, bool primary) {
+        const size_t r = build_octree_one(m, oct14, oct54, oct94, n, first_modind, paths_on_device, buftype);
+        if (primary) total = r;
+    });
+    return total;
+}
+
+size_t octree_cuc_voxelise_and_build(octree_glc_t* rc, const float* pos, const uint8_t* col_u8, const float* nrm,
+                                     size_t n, int size, int levels, int inputs_on_device, int dynamic,
+                                     int64_t* order_host, float* pos_host)
+{
+    Impl* I = impl_of(rc);
+    if (inputs_on_device && !I->replicas.empty())
+        die("voxelise_and_build: device-resident inputs belong to one GPU; a multi-GPU group takes host arrays");
+    size_t m0 = 0;
+    run_on_group(rc, [&](octree_glc_t* m, bool primary) {
+        const size_t r = voxelise_one(m, pos, col_u8, nrm, n, size, levels, inputs_on_device, dynamic,
+                                      primary ? order_host : nullptr, primary ? pos_host : nullptr);
+        if (primary) m0 = r;
+    });
+    return m0;
+}
 
 } // extern "C"
 
@@ -1813,7 +2224,10 @@ void bone_consts(const float* ob, const float* nb, int div, BoneConsts* out10)
 
 extern "C" {
 
-void octree_cuc_skeleton_alloc_in(octree_glc_t* rc, const float* pntdata, const float* nrmdata, size_t bytes)
+} // extern "C"
+namespace
+{
+void skeleton_alloc_one(octree_glc_t* rc, const float* pntdata, const float* nrmdata, size_t bytes)
 {
     Impl*        I = impl_of(rc);
     const size_t n = bytes / 12;
@@ -1837,8 +2251,8 @@ void octree_cuc_skeleton_alloc_in(octree_glc_t* rc, const float* pntdata, const 
     publish_memsize(rc, I);
 }
 
-size_t octree_cuc_skeleton_update(octree_glc_t* rc, const float* oldbones80, const float* newbones80, int model_count,
-                                  int maxlevel, float basesize, int build_tree)
+size_t skeleton_update_one(octree_glc_t* rc, const float* oldbones80, const float* newbones80, int model_count,
+                           int maxlevel, float basesize, int build_tree)
 {
     Impl* I = impl_of(rc);
     if (model_count < 0 || (size_t) model_count > I->skin_n) die("skeleton_update: more points than skeleton_alloc_in gave");
@@ -1879,12 +2293,36 @@ size_t octree_cuc_skeleton_update(octree_glc_t* rc, const float* oldbones80, con
     publish_memsize(rc, I);
     return nodes;
 }
+} // namespace
+
+extern "C" {
+
+void octree_cuc_skeleton_alloc_in(octree_glc_t* rc, const float* pntdata, const float* nrmdata, size_t bytes)
+{
+    impl_of(rc);
+    run_on_group(rc, [=](octree_glc_t* m, bool) { skeleton_alloc_one(m, pntdata, nrmdata, bytes); });
+}
+
+// Every device of a group skins and builds for itself: the inputs are 160 floats, the outputs (the dynamic tree and
+// 10 M normals) would be hundreds of megabytes to send around, and the kernels are deterministic.
+size_t octree_cuc_skeleton_update(octree_glc_t* rc, const float* oldbones80, const float* newbones80, int model_count,
+                                  int maxlevel, float basesize, int build_tree)
+{
+    impl_of(rc);
+    size_t nodes = 0;
+    run_on_group(rc, [&](octree_glc_t* m, bool primary) {
+        const size_t r = skeleton_update_one(m, oldbones80, newbones80, model_count, maxlevel, basesize, build_tree);
+        if (primary) nodes = r;
+    });
+    return nodes;
+}
 
 void octree_cuc_skeleton_set_rotations(octree_glc_t* rc, const float* rotations90)
 {
     Impl* I         = impl_of(rc);
     I->skin_rot_set = rotations90 != nullptr;
     if (rotations90) memcpy(I->skin_rot, rotations90, sizeof(I->skin_rot));
+    REPLAY(I, octree_cuc_skeleton_set_rotations(m, rotations90));
 }
 
 size_t octree_cuc_skeleton_read_out(octree_glc_t* rc, int32_t* oct14, int32_t* oct54, int32_t* oct94, float* nrm_out,
@@ -2092,17 +2530,28 @@ void octree_cuc_debug_order_lut(uint64_t* out4096)
 }
 
 // blob = { uint64 ndesc, uint64 payload_bytes, RangeDesc[ndesc], payload }
+void octree_cuc_enable_replication_log(octree_glc_t* rc, int on)
+{
+    Impl* I    = impl_of(rc);
+    I->repl_on = on != 0;
+    I->repl_descs.clear();
+    I->repl_payload.clear();
+}
+
 size_t octree_cuc_export_pending(octree_glc_t* rc, void* blob_host, size_t capacity)
 {
-    Impl*  I    = impl_of(rc);
-    size_t nd   = I->descs.size();
-    size_t need = 16 + nd * sizeof(RangeDesc) + I->batch_used;
+    Impl* I = impl_of(rc);
+    if (!I->repl_on) die("export_pending: call octree_cuc_enable_replication_log first (ranges already applied are gone)");
+    const size_t nd   = I->repl_descs.size();
+    const size_t need = 16 + nd * sizeof(RangeDesc) + I->repl_payload.size();
     if (blob_host == nullptr || capacity < need) return need;
-    uint64_t hdr[2] = {(uint64_t) nd, (uint64_t) I->batch_used};
+    uint64_t hdr[2] = {(uint64_t) nd, (uint64_t) I->repl_payload.size()};
     char*    p      = (char*) blob_host;
     memcpy(p, hdr, 16);
-    memcpy(p + 16, I->descs.data(), nd * sizeof(RangeDesc));
-    memcpy(p + 16 + nd * sizeof(RangeDesc), I->batch_host, I->batch_used);
+    if (nd) memcpy(p + 16, I->repl_descs.data(), nd * sizeof(RangeDesc));
+    if (!I->repl_payload.empty()) memcpy(p + 16 + nd * sizeof(RangeDesc), I->repl_payload.data(), I->repl_payload.size());
+    I->repl_descs.clear();
+    I->repl_payload.clear();
     return need;
 }
 
@@ -2113,20 +2562,30 @@ void octree_cuc_apply_blob(octree_glc_t* rc, const void* blob_host, size_t bytes
     const char* p = (const char*) blob_host;
     uint64_t    hdr[2];
     memcpy(hdr, p, 16);
-    if (16 + hdr[0] * sizeof(RangeDesc) + hdr[1] != bytes) die("apply_blob: malformed blob");
-    const RangeDesc* d       = (const RangeDesc*) (p + 16);
-    const char*      payload = p + 16 + hdr[0] * sizeof(RangeDesc);
+    if (hdr[0] > (bytes - 16) / sizeof(RangeDesc) || 16 + hdr[0] * sizeof(RangeDesc) + hdr[1] != bytes || hdr[1] % 4)
+        die("apply_blob: malformed blob");
+    const char* payload = p + 16 + hdr[0] * sizeof(RangeDesc);
+    // every descriptor is checked before anything is applied
     for (uint64_t i = 0; i < hdr[0]; i++)
     {
-        // re-enter through the batched path: `fake` is positioned so that
-        // fake + dst offset addresses this range's payload
-        size_t      s    = (size_t) d[i].dst_word * 4;
-        size_t      e    = s + (size_t) d[i].nwords * 4;
-        const char* fake = payload + (size_t) d[i].src_word * 4 - s;
-        ensure_capacity(I, d[i].buftype, e);
-        note_extent(I, d[i].buftype, e);
-        upload_batched(I, fake, d[i].buftype, s, e);
+        RangeDesc d;
+        memcpy(&d, p + 16 + i * sizeof(RangeDesc), sizeof(d));
+        if (d.buftype < 0 || d.buftype > 5) die("apply_blob: descriptor with an unknown buffer type");
+        if (d.nwords == 0 || ((uint64_t) d.src_word + d.nwords) * 4 > hdr[1]) die("apply_blob: descriptor outside the payload");
+        const uint64_t item = is_octree(d.buftype) ? 16 : 12;
+        if ((d.dst_word * 4) % item || ((uint64_t) d.nwords * 4) % item) die("apply_blob: range is not texel-aligned");
+        if (is_octree(d.buftype) && (d.dst_word + d.nwords + 11) / 12 > (uint64_t) CHILD_INDEX_MASK - 1)
+            die("apply_blob: range beyond the node limit");
     }
+    for (uint64_t i = 0; i < hdr[0]; i++)
+    {
+        RangeDesc d;
+        memcpy(&d, p + 16 + i * sizeof(RangeDesc), sizeof(d));
+        const size_t s = (size_t) d.dst_word * 4, e = s + (size_t) d.nwords * 4;
+        ensure_capacity(I, d.buftype, e);
+        apply_range(I, payload + (size_t) d.src_word * 4, d.buftype, s, e);
+    }
+    REPLAY(I, octree_cuc_apply_blob(m, blob_host, bytes));
     publish_memsize(rc, I);
 }
 

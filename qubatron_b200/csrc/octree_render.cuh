@@ -80,6 +80,86 @@ __global__ void trace_lines_kernel(const FrameParams P, size_t n, const float* _
     }
 }
 
+// ---------------------------------------------------------------------------
+// multi-GPU completion fence (FenceDev, octree_types.cuh): device-side flags instead of a collective per frame
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+constexpr long long FENCE_TIMEOUT_CYCLES = 8000000000ll; // ~4 s: a peer that never answers traps instead of hanging
+__device__ __noinline__ void fence_spin(const unsigned* p, unsigned want)
+{
+    const long long t0 = clock64();
+    while ((int) (ld_acquire_sys(p) - want) < 0)
+    {
+        __nanosleep(64);
+        if (clock64() - t0 > FENCE_TIMEOUT_CYCLES)
+        {
+            printf("octree_cuc: multi-GPU fence timed out waiting for frame %u (have %u)\n", want, ld_acquire_sys(p));
+            __trap();
+        }
+    }
+}
+// rank 0, first CTA of the frame's kernel: everything queued on rank 0's stream before this kernel has finished, so
+// the previous frame has been consumed and the peers may overwrite it
+__device__ __forceinline__ void fence_prologue(const FenceDev& F)
+{
+    if (F.peers && blockIdx.x == 0 && threadIdx.x > 0 && threadIdx.x < (unsigned) F.n)
+        st_release_sys(F.peers[threadIdx.x] + FENCE_CONSUMED, F.seq - 1u);
+}
+// ranks != 0, before a warp's pixels go into rank 0's framebuffer (the traversal itself never waits)
+__device__ __forceinline__ void fence_gate(const FenceDev& F)
+{
+    if (F.gate)
+    {
+        if ((threadIdx.x & 31) == 0) fence_spin(F.gate, F.seq - 1u);
+        __syncwarp();
+    }
+}
+// ranks != 0, after the CTA's stores: the last CTA of the launch publishes the frame number to rank 0
+__device__ __forceinline__ void fence_epilogue(const FenceDev& F)
+{
+    if (F.done)
+    {
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            const unsigned old = atomicAdd(F.cta_count, 1u);
+            if (old == gridDim.x - 1)
+            {
+                *F.cta_count = 0;
+                __threadfence_system();
+                st_release_sys(F.done, F.seq);
+            }
+        }
+    }
+}
+// the same signals for a rank that has no tile of the frame (or no kernel to put them in)
+__global__ void fence_signal_kernel(FenceDev F)
+{
+    if (F.peers && threadIdx.x > 0 && threadIdx.x < (unsigned) F.n)
+        st_release_sys(F.peers[threadIdx.x] + FENCE_CONSUMED, F.seq - 1u);
+    if (F.done && threadIdx.x == 0)
+    {
+        fence_spin(F.gate, F.seq - 1u);
+        __threadfence_system();
+        st_release_sys(F.done, F.seq);
+    }
+}
+// rank 0, after its own kernel: wait until every rank has published this frame
+__global__ void fence_wait_done_kernel(const unsigned* local, int n, unsigned seq)
+{
+    if (threadIdx.x > 0 && threadIdx.x < (unsigned) n) fence_spin(local + threadIdx.x, seq);
+}
+
 // order[r] = the tile with the r-th largest cost (ties in tile order); clears the cost array of the next frame
 __global__ void tile_rank_kernel(const unsigned* __restrict__ cost, int n, int* __restrict__ order,
                                  unsigned* __restrict__ next_cost)
@@ -138,6 +218,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) render_kernel(const FrameParams
         for (int i = 0; i < CNT_COUNT; i++) cnt.v[i] = 0;
     }
 
+    fence_prologue(P.fence);
     const bool active = px < P.W && py < P.H;
     if (active)
     {
@@ -259,6 +340,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) render_kernel(const FrameParams
             if (COUNT) cnt.v[CNT_DISCARDS]++;
         }
 
+        if (P.fence.gate) fence_spin(P.fence.gate, P.fence.seq - 1u);
         const size_t p = (size_t) view * P.view_stride + (size_t) py * P.pitch + px;
         P.frame[p]     = make_uchar4((unsigned char) unorm8(cr), (unsigned char) unorm8(cg), (unsigned char) unorm8(cb),
                                      (unsigned char) unorm8(ca));
@@ -287,6 +369,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) render_kernel(const FrameParams
             if ((threadIdx.x & 31) == 0 && v) atomicAdd(P.counters + i, (unsigned long long) v);
         }
     }
+    fence_epilogue(P.fence);
 }
 
 } // namespace qb

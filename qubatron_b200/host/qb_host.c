@@ -75,6 +75,28 @@ void qb_octree_reset(qb_octree* t)
     t->len = 1;
 }
 
+/* take over an existing node array (a level loaded from its flat file, model.c L53-111) */
+void qb_octree_adopt(qb_octree* t, const int32_t* nodes, int64_t n)
+{
+    tree_reserve(t, n + n / 8 + 1024);
+    memcpy(t->nodes, nodes, (size_t) n * QB_NODE_INTS * sizeof(int32_t));
+    t->len = n;
+}
+
+/* The engine's loop over the nodes a shot touched (modelutil.c L429-437, L486-501): one
+ * octree_glc_upload_texbuffer_data call per 48-byte node, `data` = the whole node array.  `upload` is that entry
+ * point of the connector in use (this library stays independent of it). */
+typedef void (*qb_upload_fn)(void* rc, void* data, int type, size_t size, size_t itemsize, size_t start, size_t end,
+                             int buftype);
+void qb_upload_node_ranges(qb_upload_fn upload, void* rc, qb_octree* t, const int32_t* node_index, int64_t count,
+                           int buftype)
+{
+    const size_t node = QB_NODE_INTS * sizeof(int32_t);
+    for (int64_t i = 0; i < count; i++)
+        upload(rc, t->nodes, 0x1404 /* GL_INT */, (size_t) t->len * node, 4 * sizeof(int32_t),
+               (size_t) node_index[i] * node, (size_t) (node_index[i] + 1) * node, buftype);
+}
+
 int64_t  qb_octree_len(const qb_octree* t) { return t->len; }
 int32_t* qb_octree_nodes(qb_octree* t) { return t->nodes; }
 

@@ -6,7 +6,7 @@ imbalance), and the only per-frame exchange is the assembly of the tiles:
 
   gather="p2p"   rank 0 exports its framebuffer as a CUDA IPC handle; the other ranks map it and their render
                  kernels store their pixels straight into it over NVLink (peer stores), so the transfer overlaps
-                 the traversal; one tiny all-reduce per frame is the completion fence.
+                 the traversal; completion is a device-side flag per rank (octree_cuc_set_fence), no collective.
   gather="nccl"  every rank renders into a zero-initialised full-size buffer of its own and the frame is the
                  NCCL reduce(SUM) of the buffers viewed as int32 (tiles are disjoint, so the sum is the union).
 
@@ -89,7 +89,15 @@ def broadcast_blob(blob, src=0, device=None):
 
 
 class ShardedFrame:
-    """Frame assembly for N ranks around one OctreeGlc per rank (used by bench.py and the multi-GPU tests)."""
+    """Frame assembly for N ranks (one process per GPU, torchrun) around one OctreeGlc per rank; used by bench.py and
+    the multi-GPU tests.  A C host that owns all the GPUs of a box in one process uses octree_cuc_set_gpus instead,
+    which wires the same mechanism inside the connector.  This class only exchanges CUDA IPC handles:
+
+      gather="p2p"         peer stores into rank 0's framebuffer, completed by the connector's device-side fence
+                           (octree_cuc_set_fence): no collective in the frame path at all
+      gather="p2p_nccl"    the same stores fenced by one 4-byte NCCL all-reduce per frame (round 1, kept for A/B)
+      gather="nccl"        every rank renders into its own zeroed buffer, frame = NCCL reduce(SUM)
+    """
 
     def __init__(self, rc, width, height, rank, world, device, gather="p2p", tile=64):
         import torch
@@ -98,6 +106,7 @@ class ShardedFrame:
         self.width, self.height = width, height
         self.dist, self.torch = dist, torch
         self.peer_ptr = 0
+        self.opened = []
         self.frame_t = None
         self.out_t = None
         self.fence = torch.zeros(1, device=device)
@@ -105,13 +114,31 @@ class ShardedFrame:
         if world == 1:
             return
         rc.reserve_frame(width, height, 1)
-        if gather == "p2p":
+        if rank == 0:
+            rc.enable_replication_log(True)   # range uploads from here on are exported by broadcast_updates
+        if gather in ("p2p", "p2p_nccl"):
             h = torch.from_numpy(rc.ipc_export_frame().copy()).to(device) if rank == 0 else torch.zeros(
                 64, dtype=torch.uint8, device=device)
             dist.broadcast(h, 0)
             if rank != 0:
                 self.peer_ptr = rc.ipc_open(h.cpu().numpy())
+                self.opened.append(self.peer_ptr)
                 rc.set_frame_target(self.peer_ptr, width)
+            if gather == "p2p":
+                own = rc.fence_device()
+                mine = torch.from_numpy(rc.ipc_export_ptr(own).copy()).to(device)
+                every = [torch.zeros(64, dtype=torch.uint8, device=device) for _ in range(world)]
+                dist.all_gather(every, mine)
+                ptrs = []
+                for k in range(world):
+                    if k == rank:
+                        ptrs.append(own)
+                    else:
+                        ptrs.append(rc.ipc_open(every[k].cpu().numpy()))
+                        self.opened.append(ptrs[-1])
+                dist.barrier()
+                rc.set_fence(rank, world, ptrs)
+                dist.barrier()            # nobody renders before every rank's words are zeroed and wired
         elif gather == "nccl":
             self.frame_t = torch.zeros((height, width), dtype=torch.int32, device=device)
             # rank 0 reduces into a second buffer: an in-place reduce would leave the other ranks' tiles in
@@ -123,9 +150,9 @@ class ShardedFrame:
 
     def assemble(self):
         """Queue the per-frame exchange on the current stream (after the rank's render)."""
-        if self.world == 1:
-            return
-        if self.gather == "p2p":
+        if self.world == 1 or self.gather == "p2p":
+            return                            # the fence is part of octree_glc_update
+        if self.gather == "p2p_nccl":
             self.dist.all_reduce(self.fence)  # every rank's peer stores for this frame are complete after this
         else:
             if self.rank == 0:
@@ -135,8 +162,10 @@ class ShardedFrame:
                 self.dist.reduce(self.frame_t, 0, op=self.dist.ReduceOp.SUM)
 
     def read_frame(self, out=None):
-        """Rank 0: the assembled RGBA8 frame as uint8 [H,W,4] (synchronises)."""
-        if self.world == 1 or self.gather == "p2p":
+        """Rank 0: the assembled RGBA8 frame as uint8 [H,W,4] (synchronises rank 0's stream).  With gather="p2p" the
+        other ranks cannot overwrite the frame before rank 0's next update; with "p2p_nccl" the caller must keep them
+        from rendering the next frame until this returns (a barrier)."""
+        if self.world == 1 or self.gather in ("p2p", "p2p_nccl"):
             return self.rc.read_frame(out)
         host = self.out_t.cpu().numpy().view(np.uint8).reshape(self.height, self.width, 4)
         if out is not None:
@@ -145,22 +174,23 @@ class ShardedFrame:
         return host
 
     def read_frame_async(self, out=None):
-        """COLLECTIVE (call on every rank after assemble()): rank 0 queues the copy of the assembled frame into `out`
-        (page-locked uint8 [H,W,4]) so that it overlaps the next frame; finish with rc.wait_reads() on rank 0.
-        p2p gather: rank 0 snapshots its framebuffer into a staging buffer on the render stream (a few us), then a
-        second fence keeps the other ranks from storing the NEXT frame's tiles into it before that snapshot is
-        taken; the host copy runs from the staging buffer on the copy stream."""
+        """Call on every rank after assemble(): rank 0 queues the copy of the assembled frame into `out` (page-locked
+        uint8 [H,W,4]) so that it overlaps the next frame; finish with rc.wait_reads() on rank 0.
+        Rank 0 snapshots its framebuffer into a staging buffer on the render stream (a few us) and the host copy runs
+        from there on the copy stream.  gather="p2p": the other ranks' next stores wait for rank 0's next kernel,
+        which is queued behind the snapshot -- nothing else to do.  "p2p_nccl": a second all-reduce."""
         if self.world == 1:
             return self.rc.read_frame_async(out)
-        if self.gather != "p2p":
+        if self.gather == "nccl":
             return self.read_frame(out) if self.rank == 0 else None
         if self.rank == 0:
             self.rc.read_frame_staged(out)
-        self.dist.all_reduce(self.fence)
+        if self.gather == "p2p_nccl":
+            self.dist.all_reduce(self.fence)
         return out
 
     def broadcast_updates(self, device):
-        """Rank 0's pending range uploads -> every rank (rank 0 applies its own at the next frame)."""
+        """Rank 0's range uploads since the last call -> every rank (rank 0 has applied its own already)."""
         if self.world == 1:
             return 0
         blob = self.rc.export_pending() if self.rank == 0 else None
@@ -170,6 +200,13 @@ class ShardedFrame:
         return len(blob)
 
     def close(self):
+        if self.world > 1 and self.gather == "p2p":
+            self.rc.sync()
+            self.dist.barrier()
+            self.rc.set_fence(0, 1, None)
         if self.peer_ptr:
-            self.rc.ipc_close(self.peer_ptr)
-            self.peer_ptr = 0
+            self.rc.set_frame_target(0, 0)
+        for p in self.opened:
+            self.rc.ipc_close(p)
+        self.opened = []
+        self.peer_ptr = 0

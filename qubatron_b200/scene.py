@@ -42,6 +42,8 @@ def host_lib():
     lib.qb_octree_insert_points.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]
     lib.qb_octree_insert_paths.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]
     lib.qb_octree_remove_point.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.qb_octree_adopt.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+    lib.qb_upload_node_ranges.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
     lib.qb_voxelise_order.restype = C.c_int64
     lib.qb_voxelise_order.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.qb_gather_f3.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
@@ -76,6 +78,19 @@ class HostOctree:
         self.lib.qb_octree_insert_point(self.h, p.ctypes.data_as(C.c_void_p), int(modind),
                                         touched.ctypes.data_as(C.c_void_p))
         return touched
+
+    def adopt(self, nodes):
+        """Take over an existing int32 [n,12] node array (e.g. a level's flat file) instead of re-inserting."""
+        nodes = np.ascontiguousarray(nodes, dtype=np.int32).reshape(-1, 12)
+        self.lib.qb_octree_adopt(self.h, nodes.ctypes.data_as(C.c_void_p), len(nodes))
+
+    def upload_node_ranges(self, rc, node_index, buftype):
+        """The engine's per-node upload loop (modelutil.c L429-437) in C: one octree_glc_upload_texbuffer_data call
+        per touched node through the connector `rc` (an OctreeGlc)."""
+        idx = np.ascontiguousarray(node_index, dtype=np.int32)
+        fn = C.cast(rc.lib.octree_glc_upload_texbuffer_data, C.c_void_p)
+        self.lib.qb_upload_node_ranges(fn, C.cast(rc._p, C.c_void_p), self.h, idx.ctypes.data_as(C.c_void_p), len(idx),
+                                       int(buftype))
 
     def insert_paths(self, paths, first_modind=0):
         paths = np.ascontiguousarray(paths, dtype=np.int32).reshape(-1, 12)

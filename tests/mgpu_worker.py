@@ -6,6 +6,7 @@ Checks, against the CPU oracle on rank 0:
 """
 import os
 import sys
+import zlib
 
 import numpy as np
 import torch
@@ -32,7 +33,8 @@ def main():
     W, H = 300, 170
     pos, ang = (760.0, 200.0, 420.0), (-0.05, -0.12, 0.0)
     ok = True
-    for gather in ("p2p", "nccl"):
+    frame_crc = None
+    for gather in ("p2p", "p2p_nccl", "nccl"):
         rc = K.OctreeGlc(b"", device=local)
         rc.set_stream(stream.cuda_stream)
         rc.upload_scene(sc)
@@ -45,6 +47,10 @@ def main():
         if rank == 0:
             got = sh.read_frame()
             ref = O.render(O.OracleScene(sc), O.uniforms(W, H, pos, ang, shoot=0))
+            crc = zlib.crc32(got.tobytes())
+            if frame_crc is None:
+                frame_crc = crc
+            ok = ok and crc == frame_crc                 # every gather assembles the same bytes
             d = int(np.abs(got.astype(np.int16) - ref["rgba"].astype(np.int16)).max())
             print("gather=%s world=%d max rgba diff %d" % (gather, world, d), flush=True)
             ok = ok and d <= parity.RGB_TOL
@@ -93,8 +99,9 @@ def main():
                     rc.upload_texbuffer_data(nodes, K.GL_INT, len(nodes) * 48, 16, o * 48, (o + 1) * 48,
                                              K.STATIC_OCTREE)
                     col[m] = (1.0, 0.0, 1.0)
-            lo, hi = int(near.min()), int(near.max()) + 1
-            rc.upload_points(col, K.STATIC_COLOR, lo, hi)
+            # the whole colour array (360 KB): a BULK range, which flushes the queued node ranges on rank 0 --
+            # the replication log must carry both
+            rc.upload_points(col, K.STATIC_COLOR, 0, len(col))
         nbytes = sh.broadcast_updates(dev)
         rc.update(W, H, pos, ang)
         sh.assemble()
