@@ -821,6 +821,16 @@ def _main():
         rc.set_tile_feedback(1)
         extras["tile_feedback_off"] = {"ms_per_step": float(off.mean()), "note": "tiles in image order (QB_TILE_FEEDBACK=0)"}
         extras["moving_camera"] = leg_moving_camera(rig, poses)
+        # north_star design point 1 as an A/B: an L2 persisting access-policy window over the head of the static
+        # node array (as much as the device allows), same timed loop, L2 flushed before every step
+        rc.set_persisting_window(96 << 20)
+        win = rig.timed(poses, args.steps, warmup=len(poses))
+        rc.set_persisting_window(0)
+        rig.timed(poses, 0, warmup=2)
+        extras["l2_persisting_window"] = {"ms_per_step": float(win.mean()), "persist_mb_requested": 96,
+                                          "note": "octree_cuc_set_persisting_window(96 MB): the timed loop with the "
+                                                  "window on; compare ms_per_step of the headline (window off) and "
+                                                  "extras.warm_l2 (nothing flushed at all)"}
         if WIDTH == 1920:
             # configs[2]: the same level at 3840x2160 by image tiles
             rig.shard(3840, 2160)

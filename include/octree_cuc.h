@@ -308,6 +308,13 @@ size_t octree_cuc_skeleton_read_out(octree_glc_t* rc, int32_t* oct14, int32_t* o
  * at the end of the launch.  Pixels are independent: the frame is bit-identical either way. */
 void octree_cuc_set_tile_feedback(octree_glc_t* rc, int on);
 
+/* L2 residency A/B switch (BASELINE north_star design point 1, "hot upper levels ... in L2-persisting windows"): sets
+ * aside `persist_bytes` of L2 (clamped to the device maximum) and marks the head of the static tree's node array -- as
+ * much of it as the device's access-policy window allows -- persisting on the stream the frames run on, with the hit
+ * ratio that fits the set-aside.  0 removes the window.  Frames are identical either way; what it buys is measured
+ * in DESIGN.md (nothing on one GPU, where the node loads hit L1 94-98 % of the time). */
+void octree_cuc_set_persisting_window(octree_glc_t* rc, size_t persist_bytes);
+
 /* "Next" row (second half): the presentation pass of octree_glc_update (octree_glc.c L308-351).  With
  * present enabled every single-view, unsharded octree_glc_update also produces what the reference leaves in the
  * window's back buffer: the frame drawn LINEAR-filtered into (int)width x (int)height pixels (all four channels),

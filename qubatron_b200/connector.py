@@ -92,6 +92,7 @@ _PROTOS = {
                                                   C.c_void_p, C.c_void_p]),
     "octree_cuc_read_frame_staged": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_void_p, C.c_size_t]),
     "octree_cuc_set_tile_feedback": (None, [C.POINTER(octree_glc_t), C.c_int]),
+    "octree_cuc_set_persisting_window": (None, [C.POINTER(octree_glc_t), C.c_size_t]),
     "octree_cuc_enable_present": (None, [C.POINTER(octree_glc_t), C.c_int]),
     "octree_cuc_read_window": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_void_p, C.c_size_t, C.POINTER(C.c_int),
                                             C.POINTER(C.c_int)]),
@@ -403,6 +404,9 @@ class OctreeGlc:
 
     def set_tile_feedback(self, on=True):
         self.lib.octree_cuc_set_tile_feedback(self._p, int(bool(on)))
+
+    def set_persisting_window(self, persist_bytes):
+        self.lib.octree_cuc_set_persisting_window(self._p, int(persist_bytes))
 
     def enable_present(self, on=True):
         self.lib.octree_cuc_enable_present(self._p, int(bool(on)))

@@ -57,11 +57,19 @@ using namespace qb;
 // which is device node 1 (octree_types.cuh); child words keep the DEVICE index (reference index + 1, 0 = absent) in
 // bits 0-27; the node's child-exists mask lives in the top nibble of words 0 and 1.  Atomics on disjoint bit fields
 // make concurrent updates of one node by several threads safe.
-__device__ __forceinline__ void put_node_word(int* child, int* model, size_t node, int slot, int v)
+// A child word that points past the device array (`max_dev` = its last device index) can only come from an
+// inconsistent host tree; it is stored as "the dummy" -- the fast kernel follows child words without a bounds test.
+// The child-exists bit keeps the reference's meaning (index > 0): such a candidate is kept and leads nowhere.
+__device__ __forceinline__ unsigned device_child(int v, unsigned max_dev)
+{
+    const unsigned idx = v > 0 ? (((unsigned) v + 1u) & CHILD_INDEX_MASK) : 0u;
+    return idx <= max_dev ? idx : 0u;
+}
+__device__ __forceinline__ void put_node_word(int* child, int* model, size_t node, int slot, int v, unsigned max_dev)
 {
     if (slot < 8)
     {
-        const unsigned idx  = v > 0 ? (((unsigned) v + 1u) & CHILD_INDEX_MASK) : 0u;
+        const unsigned idx  = device_child(v, max_dev);
         unsigned*      w    = (unsigned*) child + node * 8 + slot;
         unsigned*      mw   = (unsigned*) child + node * 8 + (slot >> 2);
         const unsigned bit  = 1u << (CHILD_MASK_SHIFT + (slot & 3));
@@ -83,25 +91,25 @@ __device__ __forceinline__ void put_node_word(int* child, int* model, size_t nod
 
 // words [first_word, first_word + nwords) of a 12-int node array -> child/model
 __global__ void relayout_octree_kernel(const int* __restrict__ src, size_t first_word, size_t nwords,
-                                       int* __restrict__ child, int* __restrict__ model)
+                                       int* __restrict__ child, int* __restrict__ model, unsigned max_dev)
 {
     size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
     if (i >= nwords) return;
     size_t k    = first_word + i;
     size_t node = k / 12;
-    put_node_word(child, model, node, (int) (k - node * 12), src[i]);
+    put_node_word(child, model, node, (int) (k - node * 12), src[i], max_dev);
 }
 
 // whole nodes (the common bulk case): one thread converts one 48-byte node
 __global__ void relayout_octree_nodes_kernel(const int4* __restrict__ src, size_t first_node, size_t nnodes,
-                                             int4* __restrict__ child, int* __restrict__ model)
+                                             int4* __restrict__ child, int* __restrict__ model, unsigned max_dev)
 {
     size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
     if (i >= nnodes) return;
     int4 a = src[3 * i], b = src[3 * i + 1], c = src[3 * i + 2];
     unsigned m = (a.x > 0 ? 1u : 0u) | (a.y > 0 ? 2u : 0u) | (a.z > 0 ? 4u : 0u) | (a.w > 0 ? 8u : 0u) |
                  (b.x > 0 ? 16u : 0u) | (b.y > 0 ? 32u : 0u) | (b.z > 0 ? 64u : 0u) | (b.w > 0 ? 128u : 0u);
-    auto ix = [](int v) { return v > 0 ? (int) (((unsigned) v + 1u) & CHILD_INDEX_MASK) : 0; }; // device index
+    auto ix = [max_dev](int v) { return (int) device_child(v, max_dev); }; // device index
     int4 lo = make_int4(ix(a.x) | (int) ((m & 15u) << CHILD_MASK_SHIFT), ix(a.y) | (int) ((m >> 4) << CHILD_MASK_SHIFT),
                         ix(a.z), ix(a.w));
     int4 hi = make_int4(ix(b.x), ix(b.y), ix(b.z), ix(b.w));
@@ -135,9 +143,10 @@ struct RangeDesc
 };
 struct ScatterTargets
 {
-    int*   child[2];
-    int*   model[2];
-    float* rec[2];
+    int*     child[2];
+    int*     model[2];
+    float*   rec[2];
+    unsigned max_dev[2]; // last device node index of each tree's arrays
 };
 __global__ void scatter_ranges_kernel(const RangeDesc* __restrict__ descs, int ndesc, const int* __restrict__ payload,
                                       unsigned int total_words, ScatterTargets T)
@@ -163,7 +172,7 @@ __global__ void scatter_ranges_kernel(const RangeDesc* __restrict__ descs, int n
         {
             int    t    = d.buftype == OCTREE_GLC_BUFFER_DYNAMIC_OCTREE;
             size_t node = k / 12;
-            put_node_word(T.child[t], T.model[t], node, (int) (k - node * 12), v);
+            put_node_word(T.child[t], T.model[t], node, (int) (k - node * 12), v, T.max_dev[t]);
             break;
         }
         default:
@@ -199,6 +208,8 @@ struct Tree
     // where the upload / build / export kernels see reference node 0
     int* up_child() const { return (int*) child.ptr + 8; }
     int* up_model() const { return (int*) model.ptr + 1; }
+    // last device node index the arrays hold (device nodes: cap_nodes + 2)
+    unsigned max_dev() const { return (unsigned) (cap_nodes + 1); }
 };
 struct Points
 {
@@ -329,6 +340,12 @@ struct Impl
     int         fence_rank = 0, fence_n = 1;
     unsigned    fence_seq  = 0;
     cudaEvent_t ev_done    = nullptr; // rank 0: every rank's tiles of the last frame are in the framebuffer
+    size_t                l2_window_bytes  = 0; // octree_cuc_set_persisting_window
+    cudaStream_t          l2_window_stream = nullptr;
+    const void*           l2_window_base   = nullptr;
+    bool                  l2_window_dirty  = false;
+    bool                  defer_completion = false; // group primary: see render_views / group_render
+    std::function<void()> deferred;
     // in-process multi-GPU group (octree_cuc_set_gpus): the connectors of the other devices, driven by the same calls
     std::vector<octree_glc_t> replicas;
     bool                      is_replica = false;
@@ -435,6 +452,7 @@ ScatterTargets scatter_targets(Impl* I)
         T.child[t] = I->tree[t].up_child();
         T.model[t] = I->tree[t].up_model();
         T.rec[t]   = (float*) I->pts[t].rec.ptr;
+        T.max_dev[t] = I->tree[t].max_dev();
     }
     return T;
 }
@@ -530,11 +548,13 @@ void upload_bulk(Impl* I, const char* src, int buftype, size_t s, size_t e)
         {
             size_t nn = n / 48;
             relayout_octree_nodes_kernel<<<(unsigned) ((nn + 255) / 256), 256, 0, I->stream>>>(
-                (const int4*) I->stage_dev, off / 48, nn, (int4*) I->tree[t].up_child(), I->tree[t].up_model());
+                (const int4*) I->stage_dev, off / 48, nn, (int4*) I->tree[t].up_child(), I->tree[t].up_model(),
+                I->tree[t].max_dev());
         }
         else if (is_octree(buftype))
             relayout_octree_kernel<<<blocks, 256, 0, I->stream>>>((const int*) I->stage_dev, off / 4, words,
-                                                                  I->tree[t].up_child(), I->tree[t].up_model());
+                                                                  I->tree[t].up_child(), I->tree[t].up_model(),
+                                                                  I->tree[t].max_dev());
         else
         {
             int which = (buftype == OCTREE_GLC_BUFFER_STATIC_NORMAL || buftype == OCTREE_GLC_BUFFER_DYNAMIC_NORMAL);
@@ -829,6 +849,42 @@ void ensure_aux(Impl* I, size_t total)
     I->memsize += I->aux_cap * 25;
 }
 
+// octree_cuc_set_persisting_window: see include/octree_cuc.h
+void apply_l2_window(Impl* I)
+{
+    const void* base = I->tree[0].child.ptr;
+    if (!I->l2_window_dirty && I->l2_window_stream == I->stream && I->l2_window_base == base) return;
+    if (!I->l2_window_bytes && !I->l2_window_dirty) return;
+    int max_persist = 0, max_window = 0;
+    CUDA_OK(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, I->device));
+    CUDA_OK(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, I->device));
+    cudaStreamAttrValue a;
+    memset(&a, 0, sizeof(a));
+    if (I->l2_window_bytes && base && max_persist > 0 && max_window > 0)
+    {
+        const size_t persist = I->l2_window_bytes < (size_t) max_persist ? I->l2_window_bytes : (size_t) max_persist;
+        CUDA_OK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist));
+        size_t win = (I->tree[0].nodes + 2) * 32;
+        if (win > (size_t) max_window) win = (size_t) max_window;
+        a.accessPolicyWindow.base_ptr  = const_cast<void*>(base);
+        a.accessPolicyWindow.num_bytes = win;
+        a.accessPolicyWindow.hitRatio  = win <= persist ? 1.0f : (float) ((double) persist / (double) win);
+        a.accessPolicyWindow.hitProp   = cudaAccessPropertyPersisting;
+        a.accessPolicyWindow.missProp  = cudaAccessPropertyStreaming;
+        fprintf(stderr, "octree_cuc: L2 window %.1f MB of the static node array, %.1f MB persisting (device max %.1f / %.1f MB)\n",
+                win / 1e6, persist / 1e6, max_window / 1e6, max_persist / 1e6);
+    }
+    else
+    {
+        a.accessPolicyWindow.num_bytes = 0; // disables the window
+        if (I->l2_window_bytes == 0) cudaCtxResetPersistingL2Cache();
+    }
+    CUDA_OK(cudaStreamSetAttribute(I->stream, cudaStreamAttributeAccessPolicyWindow, &a));
+    I->l2_window_stream = I->stream;
+    I->l2_window_base   = base;
+    I->l2_window_dirty  = false;
+}
+
 void render_views(octree_glc_t* rc, int n, float width, float height, const float* positions, const float* angles,
                   float lighta, uint8_t quality, int maxlevel, float basesize, int shoot)
 {
@@ -965,6 +1021,7 @@ void render_views(octree_glc_t* rc, int n, float width, float height, const floa
     I->H       = H;
     I->n_views = n;
 
+    if (I->l2_window_bytes || I->l2_window_dirty) apply_l2_window(I);
     if (I->count_on) CUDA_OK(cudaMemsetAsync(I->counters, 0, CNT_COUNT * sizeof(unsigned long long), I->stream));
     // glClear(0,0,0,0) (octree_glc.c L289-290) needs no pass of its own: the
     // kernel stores every pixel of the tiles it owns, discarded ones as (0,0,0,0)
@@ -1065,35 +1122,44 @@ void render_views(octree_glc_t* rc, int n, float width, float height, const floa
         I->launches++;
     }
     if (!ev1_recorded) CUDA_OK(cudaEventRecord(I->ev1, I->stream));
-    if (fenced && I->fence_rank == 0)
-    {
-        // the frame is complete once every rank has published its number (peer stores + release, no collective)
-        fence_wait_done_kernel<<<1, 64, 0, I->stream>>>(I->fence_words, I->fence_n, P.fence.seq);
-        CUDA_OK(cudaGetLastError());
-        I->launches++;
-        CUDA_OK(cudaEventRecord(I->ev_done, I->stream));
-    }
-    // octree_glc.c L308-351; after ev1: not part of the frame time
-    if (I->present_on && n == 1 && (I->shard_world == 1 || (fenced && I->fence_rank == 0)))
-    {
-        const int ww = (int) width, wh = (int) height;
-        if (ww > 0 && wh > 0)
+    // What follows the frame's own kernel on this stream: the wait for the other ranks' tiles and the presentation
+    // pass.  The primary of an in-process group queues it only after every member's kernel has been launched
+    // (group_render), so that nothing the host does in between -- an allocation that synchronises the device, when
+    // members share a GPU -- can sit between the wait and the kernels it waits for.
+    const uchar4* const done_frame = P.frame;
+    const size_t        done_pitch = P.pitch;
+    const unsigned      done_seq   = P.fence.seq;
+    auto completion = [=]() {
+        const int  ww = (int) width, wh = (int) height;
+        const bool present = I->present_on && n == 1 && (I->shard_world == 1 || (fenced && I->fence_rank == 0)) &&
+                             ww > 0 && wh > 0;
+        // allocations first: nothing that may synchronise the device goes between the wait below and its peers
+        if (present && (size_t) ww * wh > I->window_cap)
         {
-            if ((size_t) ww * wh > I->window_cap)
+            if (I->window)
             {
-                if (I->window)
-                {
-                    CUDA_OK(cudaStreamSynchronize(I->stream));
-                    CUDA_OK(cudaFree(I->window));
-                    I->memsize -= I->window_cap * 4;
-                }
-                CUDA_OK(cudaMalloc(&I->window, (size_t) ww * wh * 4));
-                I->window_cap = (size_t) ww * wh;
-                I->memsize += I->window_cap * 4;
+                CUDA_OK(cudaStreamSynchronize(I->stream));
+                CUDA_OK(cudaFree(I->window));
+                I->memsize -= I->window_cap * 4;
             }
+            CUDA_OK(cudaMalloc(&I->window, (size_t) ww * wh * 4));
+            I->window_cap = (size_t) ww * wh;
+            I->memsize += I->window_cap * 4;
+        }
+        if (fenced && I->fence_rank == 0)
+        {
+            // the frame is complete once every rank has published its number (peer stores + release, no collective)
+            fence_wait_done_kernel<<<1, 64, 0, I->stream>>>(I->fence_words, I->fence_n, done_seq);
+            CUDA_OK(cudaGetLastError());
+            I->launches++;
+            CUDA_OK(cudaEventRecord(I->ev_done, I->stream));
+        }
+        // octree_glc.c L308-351; after ev1: not part of the frame time
+        if (present)
+        {
             PresentParams Q;
-            Q.frame  = P.frame;
-            Q.pitch  = P.pitch;
+            Q.frame  = done_frame;
+            Q.pitch  = done_pitch;
             Q.vp_w   = W;
             Q.vp_h   = H;
             Q.sx     = (double) ow / (double) ww;
@@ -1108,8 +1174,12 @@ void render_views(octree_glc_t* rc, int n, float width, float height, const floa
             I->window_w = ww;
             I->window_h = wh;
         }
-    }
-    if (I->ring_on && !fenced && !I->ext_target) CUDA_OK(cudaEventRecord(I->ev_render[I->ring_cur], I->stream));
+        if (I->ring_on && !fenced && !I->ext_target) CUDA_OK(cudaEventRecord(I->ev_render[I->ring_cur], I->stream));
+    };
+    if (I->defer_completion)
+        I->deferred = completion;
+    else
+        completion();
     I->timed = true;
     publish_memsize(rc, I);
 }
@@ -1144,8 +1214,15 @@ void group_render(octree_glc_t* rc, int n, float width, float height, const floa
         R->ext_aux    = I->aux_on ? I->aux : nullptr;
     }
     // the primary first: its kernel carries the "previous frame consumed" signal the others' stores wait for
+    I->defer_completion = true;
     render_views(rc, n, width, height, positions, angles, lighta, quality, maxlevel, basesize, shoot);
+    I->defer_completion = false;
     REPLAY(I, render_views(m, n, width, height, positions, angles, lighta, quality, maxlevel, basesize, shoot));
+    if (I->deferred)
+    {
+        I->deferred();
+        I->deferred = nullptr;
+    }
     // device memory of the whole group
     uint64_t mem = I->memsize;
     for (auto& r : I->replicas) mem += ((Impl*) r.impl)->memsize;
@@ -1235,6 +1312,7 @@ octree_glc_t octree_glc_init(char* path)
     CUDA_OK(cudaStreamCreateWithFlags(&I->own_stream, cudaStreamNonBlocking));
     I->stream = I->own_stream;
     if (getenv("QB_TILE_FEEDBACK")) I->feedback_on = atoi(getenv("QB_TILE_FEEDBACK")) != 0; // for A/B runs
+    if (getenv("QB_L2_WINDOW_MB")) I->l2_window_bytes = (size_t) atoi(getenv("QB_L2_WINDOW_MB")) << 20, I->l2_window_dirty = true;
     CUDA_OK(cudaEventCreate(&I->ev0));
     CUDA_OK(cudaEventCreate(&I->ev1));
     for (int i = 0; i < VIEW_RING; i++) CUDA_OK(cudaEventCreateWithFlags(&I->slot_ev[i], cudaEventDisableTiming));
@@ -1456,6 +1534,18 @@ void octree_cuc_set_tile_feedback(octree_glc_t* rc, int on)
     Impl* I        = impl_of(rc);
     I->feedback_on = on != 0;
     REPLAY(I, octree_cuc_set_tile_feedback(m, on));
+}
+
+// L2 persisting access-policy window over the head of the static tree's node array (north_star design point 1 as an
+// A/B switch): `persist_bytes` of L2 are set aside (clamped to the device maximum) and the window's lines are marked
+// persisting with the hit ratio that fits them; 0 removes the window.  Applied to the stream the frames run on.
+void octree_cuc_set_persisting_window(octree_glc_t* rc, size_t persist_bytes)
+{
+    Impl* I             = impl_of(rc);
+    I->l2_window_bytes  = persist_bytes;
+    I->l2_window_stream = nullptr; // re-apply at the next frame
+    I->l2_window_dirty  = true;
+    REPLAY(I, octree_cuc_set_persisting_window(m, persist_bytes));
 }
 
 size_t octree_cuc_read_window(octree_glc_t* rc, uint8_t* rgba_host, size_t capacity, int* width, int* height)
@@ -2397,6 +2487,14 @@ void octree_cuc_particles_update(octree_glc_t* rc, int kind, int count, int maxl
     P.basecube[0]  = 0.0f;
     P.basecube[1] = P.basecube[2] = P.basecube[3] = basesize;
     P.maxlevel                                    = maxlevel;
+    // exact grid: the fast traversal (kernel choice 1 forces the generic one, like for frames)
+    const bool   fast = I->kernel_choice != 1 && maxlevel >= 1 && grid_is_exact(basesize, maxlevel);
+    const size_t smem = (size_t) 3 * maxlevel * BLOCK_THREADS * sizeof(int);
+    if (fast)
+    {
+        P.leaf_size     = ldexpf(basesize, -maxlevel);
+        P.inv_leaf_size = 1.0f / P.leaf_size;
+    }
     const size_t n = (size_t) count;
     for (int s = 0; s < steps; s++)
     {
@@ -2404,14 +2502,22 @@ void octree_cuc_particles_update(octree_glc_t* rc, int kind, int count, int maxl
         if (kind == OCTREE_CUC_PARTICLES)
         {
             CUDA_OK(cudaMemsetAsync(I->part_finished, 0, sizeof(unsigned), st));
-            if (I->div_mode == DIV_GLSL)
-                particle_step_kernel<DIV_GLSL><<<nblk(n), 256, 0, st>>>(P, n, I->part_pos[kind][a], I->part_spd[kind][a],
-                                                                        I->part_pos[kind][b], I->part_spd[kind][b],
-                                                                        I->part_finished);
+            auto*  pa = I->part_pos[kind][a];
+            auto*  sa = I->part_spd[kind][a];
+            auto*  pb = I->part_pos[kind][b];
+            auto*  sb = I->part_spd[kind][b];
+            if (fast)
+            {
+                const unsigned g = (unsigned) ((n + BLOCK_THREADS - 1) / BLOCK_THREADS);
+                if (I->div_mode == DIV_GLSL)
+                    particle_step_kernel<DIV_GLSL, true><<<g, BLOCK_THREADS, smem, st>>>(P, n, pa, sa, pb, sb, I->part_finished);
+                else
+                    particle_step_kernel<DIV_IEEE, true><<<g, BLOCK_THREADS, smem, st>>>(P, n, pa, sa, pb, sb, I->part_finished);
+            }
+            else if (I->div_mode == DIV_GLSL)
+                particle_step_kernel<DIV_GLSL, false><<<nblk(n), 256, 0, st>>>(P, n, pa, sa, pb, sb, I->part_finished);
             else
-                particle_step_kernel<DIV_IEEE><<<nblk(n), 256, 0, st>>>(P, n, I->part_pos[kind][a], I->part_spd[kind][a],
-                                                                        I->part_pos[kind][b], I->part_spd[kind][b],
-                                                                        I->part_finished);
+                particle_step_kernel<DIV_IEEE, false><<<nblk(n), 256, 0, st>>>(P, n, pa, sa, pb, sb, I->part_finished);
         }
         else
             dust_step_kernel<<<nblk(n), 256, 0, st>>>(make_float3(campos.x, campos.y, campos.z), n, I->part_pos[kind][a],
@@ -2460,7 +2566,15 @@ void octree_cuc_trace_lines(octree_glc_t* rc, size_t n, const float* pos, const 
     CUDA_OK(cudaMemcpyAsync(d_pos, pos, n * 12, cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaMemcpyAsync(d_dir, dir, n * 12, cudaMemcpyHostToDevice, st));
     if (d_tlf) CUDA_OK(cudaMemcpyAsync(d_tlf, out_tlf, n * 16, cudaMemcpyHostToDevice, st)); // misses keep the caller's values
-    trace_lines_kernel<<<nblk(n), 256, 0, st>>>(P, n, d_pos, d_dir, d_idx, d_tlf);
+    if (I->kernel_choice != 1 && maxlevel >= 1 && grid_is_exact(basesize, maxlevel))
+    {
+        P.leaf_size     = ldexpf(basesize, -maxlevel);
+        P.inv_leaf_size = 1.0f / P.leaf_size;
+        trace_lines_fast_kernel<<<(unsigned) ((n + BLOCK_THREADS - 1) / BLOCK_THREADS), BLOCK_THREADS,
+                                  (size_t) 3 * maxlevel * BLOCK_THREADS * sizeof(int), st>>>(P, n, d_pos, d_dir, d_idx, d_tlf);
+    }
+    else
+        trace_lines_kernel<<<nblk(n), 256, 0, st>>>(P, n, d_pos, d_dir, d_idx, d_tlf);
     CUDA_OK(cudaGetLastError());
     I->launches++;
     CUDA_OK(cudaMemcpyAsync(out_index, d_idx, n * sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -10,16 +10,23 @@
 // State (position, speed: float[3] each) ping-pongs between two device buffers; nothing returns to the host unless
 // asked for.  Compiled like the renderer: no contraction, IEEE sqrt / divide, both division modes.
 #pragma once
-#include "octree_render.cuh"
+#include "octree_trace_fast.cuh"
 
 namespace qb
 {
 
-template <int DIV>
-__global__ void particle_step_kernel(const FrameParams P, size_t n, const float* __restrict__ pos,
-                                     const float* __restrict__ spd, float* __restrict__ pos_out,
-                                     float* __restrict__ spd_out, unsigned* __restrict__ finished)
+// FAST: the base cube's grid is exact in fp32 -> the trace runs through the fast traversal (shared-memory stack,
+// ordering table; trace_fast_single), except for particles with a zero speed component, whose mid-plane "hits" are
+// the particle program's vec4(0.0) sentinel; launched with BLOCK_THREADS threads and the fast kernel's shared stack.
+template <int DIV, bool FAST>
+__global__ void __launch_bounds__(FAST ? BLOCK_THREADS : 256)
+    particle_step_kernel(const FrameParams P, size_t n, const float* __restrict__ pos, const float* __restrict__ spd,
+                         float* __restrict__ pos_out, float* __restrict__ spd_out, unsigned* __restrict__ finished)
 {
+    extern __shared__ int s_stack[];
+    __shared__ unsigned   s_compact_sel[16];
+    FastSmem              fsm{0u, 0u};
+    if (FAST) fsm = fast_single_smem(s_stack, s_compact_sel);
     size_t i    = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
     bool   done = false;
     if (i < n)
@@ -30,9 +37,13 @@ __global__ void particle_step_kernel(const FrameParams P, size_t n, const float*
         if (s.x > -90000.0f) // L352
         {
             s.y -= 0.4f;
-            RayCounters       cnt;
-            const TraceResult r = trace_generic<DIV, false, TRACE_PARTICLE>(P, p, s, cnt);
-            bool              stuck = false;
+            RayCounters cnt;
+            TraceResult r;
+            if (FAST && fast_single_ok(s))
+                r = trace_fast_single<DIV, TRACE_PARTICLE>(P, p, s, fsm);
+            else
+                r = trace_generic<DIV, false, TRACE_PARTICLE>(P, p, s, cnt);
+            bool stuck = false;
             if (r.status == 1 && r.iw > 0.0f) // L358
             {
                 const float dx = r.tx - p.x, dy = r.ty - p.y, dz = r.tz - p.z;

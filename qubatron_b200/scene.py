@@ -138,6 +138,42 @@ def voxelise(pos, col_u8, nrm, size=1800, levels=LEVELS):
     return out_p, out_c, out_n
 
 
+def flat_ranges(pnt, size=1800, levels=LEVELS):
+    """The .rng stream of qmc (qmc.c L291-313): for every surviving point whose (x, y) grid column differs from the
+    previous point's -- the point before the first one counts as column (0, 0) -- one int32 triple
+    (index of the point, column x, column y).  Grid index = floor(p / precision) in fp32 (qmc.c L62-68, L217-218)."""
+    pnt = np.ascontiguousarray(pnt, dtype=np.float32).reshape(-1, 3)
+    division = 2 << int(levels)
+    precision = np.float32(size) / np.float32(division)
+    ix = np.floor(pnt[:, 0] / precision).astype(np.int32)
+    iy = np.floor(pnt[:, 1] / precision).astype(np.int32)
+    px = np.concatenate([[0], ix[:-1]]).astype(np.int32)
+    py = np.concatenate([[0], iy[:-1]]).astype(np.int32)
+    first = np.nonzero((ix != px) | (iy != py))[0]
+    return np.stack([first.astype(np.int32), ix[first], iy[first]], axis=1).astype(np.int32)
+
+
+def write_flat(prefix, pnt, nrm, col, size=1800, levels=LEVELS):
+    """The voxeliser's four output files <prefix>.pnt / .nrm / .col / .rng exactly as qmc writes them (qmc.c
+    L266-327: raw float32 x y z per point; .rng see flat_ranges) -- what model_load_flat (model.c L53-111) reads."""
+    np.ascontiguousarray(pnt, dtype=np.float32).tofile(prefix + ".pnt")
+    np.ascontiguousarray(nrm, dtype=np.float32).tofile(prefix + ".nrm")
+    np.ascontiguousarray(col, dtype=np.float32).tofile(prefix + ".col")
+    flat_ranges(pnt, size, levels).tofile(prefix + ".rng")
+
+
+def load_flat(prefix):
+    """model_load_flat (model.c L53-111): (pnt, col, nrm float32 [n,3], ranges int32 [r,3]); the point count comes
+    from the size of the .pnt file, as in the reference."""
+    pnt = np.fromfile(prefix + ".pnt", dtype=np.float32).reshape(-1, 3)
+    nrm = np.fromfile(prefix + ".nrm", dtype=np.float32).reshape(-1, 3)
+    col = np.fromfile(prefix + ".col", dtype=np.float32).reshape(-1, 3)
+    rng = np.fromfile(prefix + ".rng", dtype=np.int32).reshape(-1, 3)
+    if not (len(pnt) == len(nrm) == len(col)):
+        raise ValueError("flat model %s: .pnt / .nrm / .col hold different point counts" % prefix)
+    return pnt, col, nrm, rng
+
+
 @dataclass
 class Scene:
     name: str

@@ -1,4 +1,5 @@
-"""Particle simulation steps (particle_vsh.c) over the bench level's static tree, state kept on the device."""
+"""Particle simulation steps (particle_vsh.c) and batched CPU ray queries (octree_trace_line) over the bench level's
+static tree:  python scripts/particle_bench.py [scale] [particles] [kernel: 0 auto = fast traversal, 1 generic]"""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -20,7 +21,10 @@ stream = torch.cuda.Stream()
 torch.cuda.set_stream(stream)
 rc.set_stream(stream.cuda_stream)
 rc.upload_octree(sc.oct_s)
-out = {"particles": n, "static_nodes": int(len(sc.oct_s)), "steps": []}
+kern = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+rc.set_kernel(kern)
+out = {"particles": n, "static_nodes": int(len(sc.oct_s)), "traversal": {0: "fast (exact grid)", 1: "generic"}[kern],
+       "steps": []}
 rc.particles_alloc_in(pos, spd)
 rc.particles_update(steps=1)          # warm-up (one step of the real trajectory)
 for k in range(30):
@@ -36,5 +40,18 @@ out["first_step_ms"] = out["steps"][0]
 out["mean_step_ms"] = float(np.mean(out["steps"]))
 out["Mparticles_per_s_first_step"] = n / out["steps"][0] / 1e3
 out["host_round_trip_bytes_per_step_in_the_reference"] = 48 * n
+# batched octree_trace_line queries: the same origins, random directions; the call includes the copies of the rays
+# to the device and of the results back (44 bytes per ray)
+import time
+d = rng.normal(size=(n, 3)).astype(np.float32)
+rc.trace_lines(pos, d)
+t = []
+for _ in range(5):
+    t0 = time.time()
+    idx_out, _tlf = rc.trace_lines(pos, d)
+    t.append(time.time() - t0)
+out["trace_lines_call_ms"] = round(1e3 * float(np.median(t)), 3)
+out["trace_lines_hits"] = int((idx_out != 0).sum())
+out["trace_lines_Mrays_per_s_incl_copies"] = n / float(np.median(t)) / 1e6
 print(json.dumps(out))
 rc.destroy()

@@ -101,9 +101,19 @@ def test_voxelise_equals_reference_qmc():
         rp = np.fromfile(os.path.join(d, "t.ply.pnt"), dtype=np.float32).reshape(-1, 3)
         rn = np.fromfile(os.path.join(d, "t.ply.nrm"), dtype=np.float32).reshape(-1, 3)
         rc = np.fromfile(os.path.join(d, "t.ply.col"), dtype=np.float32).reshape(-1, 3)
-    p, c, n = S.voxelise(pos, col, nrm)
-    assert len(p) == len(rp)
-    assert np.array_equal(p, rp) and np.array_equal(n, rn) and np.array_equal(c, rc)
+        rr = open(os.path.join(d, "t.ply.rng"), "rb").read()
+        p, c, n = S.voxelise(pos, col, nrm)
+        assert len(p) == len(rp)
+        assert np.array_equal(p, rp) and np.array_equal(n, rn) and np.array_equal(c, rc)
+        # the flat-file writer (qmc.c L266-327) and reader (model.c L53-111): all four files byte for byte, incl.
+        # the column ranges of the .rng file
+        S.write_flat(os.path.join(d, "mine"), p, n, c)
+        for ext in ("pnt", "nrm", "col", "rng"):
+            assert open(os.path.join(d, "mine." + ext), "rb").read() == open(os.path.join(d, "t.ply." + ext), "rb").read(), ext
+        assert len(rr) % 12 == 0 and len(rr) > 12 * 50
+        lp, lc, ln, lr = S.load_flat(os.path.join(d, "t.ply"))
+        assert np.array_equal(lp, p) and np.array_equal(lc, c) and np.array_equal(ln, n)
+        assert lr[:, 0].max() < len(p) and np.all(np.diff(lr[:, 0]) > 0)
 
 
 def test_octree_invariants():

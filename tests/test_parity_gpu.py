@@ -400,10 +400,10 @@ def test_dynamic_tree_rebuilt_every_frame(scene_c1):
     rc.destroy()
 
 
-def test_c2_full_scale_frames_equal_the_oracle():
-    """BASELINE configs[1] at FULL size: the 95 M-point / 62 M-node level + 10 M-point figure, 1920x1080, all four
-    bench poses -- every pixel's flags (hit / shadow visibility / disc), hit indices and RGBA against the oracle
-    (which needs ~1 s per frame on the box's host cores).  Set QB_TEST_SCALE to shrink the level (same generator)."""
+@pytest.fixture(scope="module")
+def c2_level():
+    """BASELINE configs[1..4] share one level: the 95 M-point / 62 M-node static tree + the 10 M-point figure, at
+    FULL size (bench.py's cached scene; QB_TEST_SCALE shrinks it with the same generator), uploaded once."""
     import os
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -415,7 +415,14 @@ def test_c2_full_scale_frames_equal_the_oracle():
     rc.upload_scene(sc)
     rc.enable_aux(True)
     rc.enable_counters(True)
-    osc = O.OracleScene(sc)
+    yield sc, rc, O.OracleScene(sc)
+    rc.destroy()
+
+
+def test_c2_full_scale_frames_equal_the_oracle(c2_level):
+    """BASELINE configs[1] at FULL size: 1920x1080, all four bench poses -- every pixel's flags (hit / shadow
+    visibility / disc), hit indices and RGBA against the oracle (~1 s per frame on the box's host cores)."""
+    sc, rc, osc = c2_level
     for pose, (pos, ang) in enumerate(sc.cameras):
         ref = O.render(osc, O.uniforms(1920, 1080, pos, ang))
         rc.set_kernel(K.KERNEL_AUTO)
@@ -425,7 +432,85 @@ def test_c2_full_scale_frames_equal_the_oracle():
         out = parity.compare(rc.read_frame(), flags, aux, ref, what="C2 pose %d" % pose)
         assert out["rgba_maxdiff"] == 0
         assert rc.read_counters() == ref["counters"]
-    rc.destroy()
+
+
+def _compare_bands(rgba, flags, aux, osc, u, bands, div, what):
+    """the oracle renders only `bands` (row ranges) of the frame: flags and indices exact, RGBA identical there"""
+    checked = 0
+    for r0, r1 in bands:
+        ref = O.render(osc, u, rows=(r0, r1), div=div)
+        assert np.array_equal(ref["flags"][r0:r1], flags[r0:r1]), "%s rows %d-%d: flags" % (what, r0, r1)
+        assert np.array_equal(ref["aux"][r0:r1], aux[r0:r1]), "%s rows %d-%d: hit indices" % (what, r0, r1)
+        assert np.array_equal(ref["rgba"][r0:r1], rgba[r0:r1]), "%s rows %d-%d: rgba" % (what, r0, r1)
+        checked += int(((flags[r0:r1] & K.FLAG_LEAF) > 0).sum())
+    return checked
+
+
+def test_c3_2160p_frames_equal_the_oracle(c2_level):
+    """BASELINE configs[2]: the same level at 3840x2160 (a frame the reference cannot render: its FBO is 2048^2,
+    octree_glc.c L237).  Four poses, both division modes; the oracle renders three bands of 48 rows per frame (bottom
+    edge, middle, top edge), and the two kernels must agree on EVERY pixel of the frame."""
+    sc, rc, osc = c2_level
+    W, H = 3840, 2160
+    bands = [(0, 48), (1056, 1104), (H - 48, H)]
+    leafs = 0
+    for kdiv, odiv, dname in DIVS:
+        rc.set_division(kdiv)
+        for pose, (pos, ang) in enumerate(sc.cameras):
+            u = O.uniforms(W, H, pos, ang)
+            got = {}
+            for kern, name in KERNELS:
+                rc.set_kernel(kern)
+                rc.update(W, H, pos, ang)
+                assert rc.last_kernel() == kern
+                flags, aux = rc.read_aux()
+                got[name] = (rc.read_frame().copy(), flags, aux, rc.read_counters())
+            f, g = got["fast"], got["generic"]
+            for a, b, nm in zip(f[:3], g[:3], ("rgba", "flags", "aux")):
+                assert np.array_equal(a, b), "4K pose %d %s: kernels differ on %s" % (pose, dname, nm)
+            assert f[3] == g[3] and f[3]["rays_primary"] == W * H
+            leafs += _compare_bands(f[0], f[1], f[2], osc, u, bands, odiv, "4K pose %d %s" % (pose, dname))
+    rc.set_division(K.DIV_GLSL)
+    assert leafs > 200000
+
+
+def test_c5_random_views_batch_equals_the_oracle(c2_level):
+    """BASELINE configs[4]: bench.py's 64 incoherent cameras (default_rng(777)) on the full level; 8 of them rendered
+    as ONE octree_cuc_update_views batch at 1080p.  GLSL division: every pixel of every view against the oracle;
+    IEEE division: three bands per view."""
+    sc, rc, osc = c2_level
+    n = 64
+    rng = np.random.default_rng(777)
+    pos = np.stack([rng.uniform(150, 1650, n), rng.uniform(90, 330, n), rng.uniform(150, 1650, n)], axis=1)
+    ang = np.stack([rng.uniform(0, 2 * np.pi, n), rng.uniform(-0.6, 0.6, n), np.zeros(n)], axis=1)
+    pick = list(range(0, n, 8))
+    W, H = 1920, 1080
+    rc.set_kernel(K.KERNEL_AUTO)
+    leafs = 0
+    for kdiv, odiv, dname in DIVS:
+        rc.set_division(kdiv)
+        rc.update_views(W, H, pos[pick], ang[pick])
+        assert rc.last_kernel() == K.KERNEL_FAST
+        rgba = rc.read_frame(views=len(pick))
+        flags, aux = rc.read_aux(views=len(pick))
+        total = dict.fromkeys(rc.read_counters(), 0)
+        for k, v in enumerate(pick):
+            u = O.uniforms(W, H, tuple(pos[v].astype(np.float32)), tuple(ang[v].astype(np.float32)))
+            sl = slice(k * H, (k + 1) * H)
+            if odiv == O.DIV_GLSL:
+                ref = O.render(osc, u, div=odiv)
+                out = parity.compare(rgba[sl], flags[sl], aux[sl], ref, what="C5 view %d" % v)
+                assert out["rgba_maxdiff"] == 0
+                for key in total:
+                    total[key] += ref["counters"][key]
+                leafs += int(((ref["flags"] & O.FLAG_LEAF) > 0).sum())
+            else:
+                _compare_bands(rgba[sl], flags[sl], aux[sl], osc, u, [(0, 40), (520, 560), (H - 40, H)], odiv,
+                               "C5 view %d ieee" % v)
+        if odiv == O.DIV_GLSL:
+            assert rc.read_counters() == total
+    rc.set_division(K.DIV_GLSL)
+    assert leafs > 1000000
 
 
 def test_pipelined_readback_returns_the_right_frames(scene_random):
@@ -605,15 +690,18 @@ def test_skin_build_render_on_the_device_equals_the_host_pipeline(scene_c1):
     rc.destroy()
 
 
+@pytest.mark.parametrize("kern", [K.KERNEL_AUTO, K.KERNEL_GENERIC])
 @pytest.mark.parametrize("name", __import__("golden_util").PARTICLE_CASES)
-def test_particle_step_equals_the_reference_vertex_program_on_llvmpipe(name):
+def test_particle_step_equals_the_reference_vertex_program_on_llvmpipe(name, kern):
     """octree_cuc_particles_update ("next" row 8f #2) against particle_vsh.c itself (tests/golden, transform feedback
     on llvmpipe): after one step and after `steps` steps kept on the device every position and speed is
-    bit-identical; the parked count equals the host's end-of-simulation test."""
+    bit-identical; the parked count equals the host's end-of-simulation test.  Both traversals: the fast one (the
+    1800-unit cube's grid is exact; axis-parallel particles fall back per particle) and the generic one."""
     import golden_util
     g = golden_util.load_particles(name)
     steps = int(g["steps"])
     rc = K.OctreeGlc(b"", device=0)
+    rc.set_kernel(kern)
     rc.upload_octree(g["oct_s"])
     rc.particles_alloc_in(g["pos"], g["spd"])
     rc.particles_update(steps=1)
@@ -629,9 +717,11 @@ def test_particle_step_equals_the_reference_vertex_program_on_llvmpipe(name):
     rc.destroy()
 
 
+@pytest.mark.parametrize("kern", [K.KERNEL_AUTO, K.KERNEL_GENERIC])
 @pytest.mark.parametrize("div", [K.DIV_GLSL, K.DIV_IEEE])
-def test_particle_step_equals_the_oracle(scene_c1, div):
-    """Debris over the C1 room (1.3 M-node static tree), both division modes, 8 chained steps, partial counts."""
+def test_particle_step_equals_the_oracle(scene_c1, div, kern):
+    """Debris over the C1 room (1.3 M-node static tree), both division modes, both traversals, 8 chained steps,
+    partial counts."""
     rng = np.random.default_rng(17)
     n = 50000
     idx = rng.integers(0, len(scene_c1.pnt_s), n)
@@ -642,6 +732,7 @@ def test_particle_step_equals_the_oracle(scene_c1, div):
     spd[2000:3000, 2] = 0
     rc = K.OctreeGlc(b"", device=0)
     rc.set_division(div)
+    rc.set_kernel(kern)
     rc.upload_octree(scene_c1.oct_s)
     rc.particles_alloc_in(pos, spd)
     rc.particles_update(steps=8, count=n - 777)
@@ -799,6 +890,16 @@ def test_gpu_voxelise_and_bulk_build_equal_the_host_model():
     gc, gn = rc.download_points(dynamic=False)
     assert np.array_equal(gc, hc) and np.array_equal(gn, hn)
     assert np.array_equal(rc.download_octree(dynamic=False), tree.nodes())
+    # the voxeliser's flat files (qmc.c L266-327: .pnt / .nrm / .col / .rng) written from the GPU result are the
+    # bytes the host voxeliser's are (which test_host_model.py compares with the reference qmc binary's files)
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        S.write_flat(d + "/gpu", gp, gn, gc)
+        S.write_flat(d + "/host", hp, hn, hc)
+        for ext in ("pnt", "nrm", "col", "rng"):
+            assert open(d + "/gpu." + ext, "rb").read() == open(d + "/host." + ext, "rb").read(), ext
+        lp, lc, ln, lr = S.load_flat(d + "/gpu")
+        assert np.array_equal(lp, hp) and len(lr) > 100
     # and it renders like the host-built scene
     e3 = np.zeros((0, 3), np.float32)
     sc = S.Scene("gpu-qmc", hp, hc, hn, tree.nodes(), e3, e3, e3, np.zeros((1, 12), np.int32))
@@ -844,9 +945,12 @@ def test_batched_trace_lines_equal_the_reference_cpu_function(scene_c1, scene_ra
         aim = rng.integers(0, len(pts), n // 2)   # half of the rays aim at points of the model
         dd[n // 2:] = (np.asarray(pts)[aim] - org[n // 2:]).astype(np.float32)
         want_idx, want_tlf = ref.trace(org, dd)
-        got_idx, got_tlf = rc.trace_lines(org, dd, dynamic=dyn)
         assert (want_idx != 0).sum() > 5000
-        assert np.array_equal(got_idx, want_idx)
         hit = want_idx != 0
-        assert np.array_equal(got_tlf[hit], want_tlf[hit])
+        for kern in (K.KERNEL_AUTO, K.KERNEL_GENERIC):   # the fast traversal (exact grid) and the generic one
+            rc.set_kernel(kern)
+            got_idx, got_tlf = rc.trace_lines(org, dd, dynamic=dyn)
+            assert np.array_equal(got_idx, want_idx), kern
+            assert np.array_equal(got_tlf[hit], want_tlf[hit]), kern
+    rc.set_kernel(K.KERNEL_AUTO)
     rc.destroy()
