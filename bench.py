@@ -488,6 +488,8 @@ class Rig:
         ms = []
         for i in range(n):
             self.flush()
+            self.torch.cuda.synchronize()
+            self.barrier()      # ranks launch together: a rank's kernel waits (at its pixel stores) for rank 0's
             self.frame(views[i % len(views)])
             ms.append(self.rc.last_frame_ms())
         return self.max_over_ranks(ms)

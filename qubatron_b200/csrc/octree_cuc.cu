@@ -336,7 +336,6 @@ struct Impl
     unsigned*   fence_words     = nullptr; // FENCE_WORDS words on this device
     unsigned**  fence_peers_dev = nullptr; // rank 0: device table of every rank's fence words
     unsigned*   fence_peer0     = nullptr; // ranks != 0: rank 0's fence words as addressed from this device
-    unsigned*   fence_cta       = nullptr; // ranks != 0: finished-CTA counter of the running launch
     int         fence_rank = 0, fence_n = 1;
     unsigned    fence_seq  = 0;
     cudaEvent_t ev_done    = nullptr; // rank 0: every rank's tiles of the last frame are in the framebuffer
@@ -1000,7 +999,6 @@ void render_views(octree_glc_t* rc, int n, float width, float height, const floa
             if (!I->ext_target) die("update: a fenced connector of rank > 0 renders into rank 0's frame (set_frame_target)");
             P.fence.done      = I->fence_peer0 + I->fence_rank;
             P.fence.gate      = I->fence_words + FENCE_CONSUMED;
-            P.fence.cta_count = I->fence_cta;
         }
     }
 
@@ -1027,6 +1025,14 @@ void render_views(octree_glc_t* rc, int n, float width, float height, const floa
     // kernel stores every pixel of the tiles it owns, discarded ones as (0,0,0,0)
 
     const unsigned blocks = (unsigned) ((size_t) P.tiles_mine * P.blocks_per_tile_x * P.blocks_per_tile_y * n);
+    // ranks != 0 of a fence: the frame number goes to rank 0 from a 1-warp kernel right behind the render kernel
+    auto publish_done = [&]() {
+        if (!fenced || I->fence_rank == 0) return;
+        FenceDev F = P.fence;
+        F.peers    = nullptr;
+        fence_signal_kernel<<<1, 32, 0, I->stream>>>(F, 0);
+        I->launches++;
+    };
     CUDA_OK(cudaEventRecord(I->ev0, I->stream));
     bool ev1_recorded = false;
     if (blocks)
@@ -1096,6 +1102,7 @@ void render_views(octree_glc_t* rc, int n, float width, float height, const floa
         if (fast)
         {
             launch_fast(I, P, blocks);
+            publish_done();
             if (order_slot >= 0)
             {
                 // after the frame: this view's next order from the costs just measured (not part of ev0..ev1)
@@ -1109,7 +1116,10 @@ void render_views(octree_glc_t* rc, int n, float width, float height, const floa
             }
         }
         else
+        {
             launch_generic(I, P, blocks);
+            publish_done();
+        }
         CUDA_OK(cudaGetLastError());
         I->launches++;
         I->last_kernel = fast ? 2 : 1;
@@ -1117,7 +1127,7 @@ void render_views(octree_glc_t* rc, int n, float width, float height, const floa
     else if (fenced)
     {
         // no tile of this frame here: the fence signals still have to go out
-        fence_signal_kernel<<<1, 64, 0, I->stream>>>(P.fence);
+        fence_signal_kernel<<<1, 64, 0, I->stream>>>(P.fence, 1);
         CUDA_OK(cudaGetLastError());
         I->launches++;
     }
@@ -1236,8 +1246,6 @@ unsigned* fence_alloc(Impl* I)
     {
         CUDA_OK(cudaMalloc(&I->fence_words, FENCE_WORDS * sizeof(unsigned)));
         CUDA_OK(cudaMemset(I->fence_words, 0, FENCE_WORDS * sizeof(unsigned)));
-        CUDA_OK(cudaMalloc(&I->fence_cta, sizeof(unsigned)));
-        CUDA_OK(cudaMemset(I->fence_cta, 0, sizeof(unsigned)));
         CUDA_OK(cudaMalloc(&I->fence_peers_dev, 64 * sizeof(unsigned*)));
         CUDA_OK(cudaMemset(I->fence_peers_dev, 0, 64 * sizeof(unsigned*)));
         CUDA_OK(cudaEventCreate(&I->ev_done));
@@ -1259,7 +1267,6 @@ void fence_wire(Impl* I, int rank, int world, const uint64_t* ptrs)
     fence_alloc(I);
     if ((uint64_t) (uintptr_t) I->fence_words != ptrs[rank]) die("set_fence: entry `rank` must be this connector's own fence words");
     CUDA_OK(cudaMemset(I->fence_words, 0, FENCE_WORDS * sizeof(unsigned)));
-    CUDA_OK(cudaMemset(I->fence_cta, 0, sizeof(unsigned)));
     unsigned* table[64] = {};
     for (int k = 0; k < world; k++) table[k] = (unsigned*) (uintptr_t) ptrs[k];
     CUDA_OK(cudaMemcpy(I->fence_peers_dev, table, sizeof(table), cudaMemcpyHostToDevice));
@@ -1347,7 +1354,6 @@ void octree_cuc_destroy(octree_glc_t* rc)
     if (I->fence_words)
     {
         cudaFree(I->fence_words);
-        cudaFree(I->fence_cta);
         cudaFree(I->fence_peers_dev);
         cudaEventDestroy(I->ev_done);
     }

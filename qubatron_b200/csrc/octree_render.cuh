@@ -123,33 +123,19 @@ __device__ __forceinline__ void fence_gate(const FenceDev& F)
         __syncwarp();
     }
 }
-// ranks != 0, after the CTA's stores: the last CTA of the launch publishes the frame number to rank 0
-__device__ __forceinline__ void fence_epilogue(const FenceDev& F)
-{
-    if (F.done)
-    {
-        __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x == 0)
-        {
-            const unsigned old = atomicAdd(F.cta_count, 1u);
-            if (old == gridDim.x - 1)
-            {
-                *F.cta_count = 0;
-                __threadfence_system();
-                st_release_sys(F.done, F.seq);
-            }
-        }
-    }
-}
-// the same signals for a rank that has no tile of the frame (or no kernel to put them in)
-__global__ void fence_signal_kernel(FenceDev F)
+// ranks != 0, on their stream right after the render kernel: publish the frame number to rank 0.  The kernel boundary
+// orders the frame's peer stores before this kernel; it fences at system scope and release-stores the number.  (A
+// first version did this from the last CTA of the render kernel, which takes a __threadfence_system per CTA after
+// its NVLink stores: short CTAs -- the open-sky pose -- then cost more than their traversal and the pose stopped
+// scaling at all; one 1-warp launch per frame costs ~2 us.)  A rank without a tile of the frame waits for the
+// "consumed" signal itself, like its pixel stores would have.
+__global__ void fence_signal_kernel(FenceDev F, int wait_gate)
 {
     if (F.peers && threadIdx.x > 0 && threadIdx.x < (unsigned) F.n)
         st_release_sys(F.peers[threadIdx.x] + FENCE_CONSUMED, F.seq - 1u);
     if (F.done && threadIdx.x == 0)
     {
-        fence_spin(F.gate, F.seq - 1u);
+        if (wait_gate) fence_spin(F.gate, F.seq - 1u);
         __threadfence_system();
         st_release_sys(F.done, F.seq);
     }
@@ -369,7 +355,6 @@ __global__ void __launch_bounds__(BLOCK_THREADS) render_kernel(const FrameParams
             if ((threadIdx.x & 31) == 0 && v) atomicAdd(P.counters + i, (unsigned long long) v);
         }
     }
-    fence_epilogue(P.fence);
 }
 
 } // namespace qb

@@ -83,7 +83,8 @@ struct ViewParams
 
 // Multi-GPU completion fence (octree_cuc_set_fence / octree_cuc_set_gpus).  One frame is split by image tiles over
 // `n` connectors ("ranks"), all storing into rank 0's framebuffer; each connector owns FENCE_WORDS 32-bit words:
-//   word k (k < 64)       on rank 0: the last frame number rank k has finished storing (written by rank k's kernel)
+//   word k (k < 64)       on rank 0: the last frame number rank k has finished storing (written by a 1-warp kernel
+//                         that follows rank k's render kernel on its stream)
 //   word FENCE_CONSUMED   on rank k: the last frame number rank 0 is done with (written by rank 0's next kernel)
 // Frame numbers count from 1 and are compared as signed differences.  All pointers null = no fence.
 constexpr int FENCE_CONSUMED = 64;
@@ -93,7 +94,6 @@ struct FenceDev
     unsigned*        done;      // ranks != 0: where this rank publishes `seq` (word `rank` of rank 0's fence words)
     const unsigned*  gate;      // ranks != 0: own FENCE_CONSUMED word; pixel stores of frame `seq` wait for >= seq - 1
     unsigned* const* peers;     // rank 0: device table of every rank's fence words (entry 0 unused)
-    unsigned*        cta_count; // ranks != 0: CTAs of this launch that have finished (self-resetting)
     unsigned         seq;       // number of this frame
     int              n;         // ranks
 };
