@@ -315,6 +315,11 @@ void octree_cuc_set_tile_feedback(octree_glc_t* rc, int on);
  * in DESIGN.md (nothing on one GPU, where the node loads hit L1 94-98 % of the time). */
 void octree_cuc_set_persisting_window(octree_glc_t* rc, size_t persist_bytes);
 
+/* Resident CTAs per SM of the fast kernel (1..6; 0 = as many as fit, the default 7).  A frame split over many GPUs
+ * leaves each of them a shard whose time is set by its longest rays, not by throughput: with fewer warps per SM every
+ * warp runs faster.  Tuning knob, frames are identical. */
+void octree_cuc_set_occupancy(octree_glc_t* rc, int ctas_per_sm);
+
 /* "Next" row (second half): the presentation pass of octree_glc_update (octree_glc.c L308-351).  With
  * present enabled every single-view, unsharded octree_glc_update also produces what the reference leaves in the
  * window's back buffer: the frame drawn LINEAR-filtered into (int)width x (int)height pixels (all four channels),
@@ -394,6 +399,10 @@ double octree_cuc_take_upload_ms(octree_glc_t* rc);
 void   octree_cuc_enable_replication_log(octree_glc_t* rc, int on);
 size_t octree_cuc_export_pending(octree_glc_t* rc, void* blob_host, size_t capacity);
 void   octree_cuc_apply_blob(octree_glc_t* rc, const void* blob_host, size_t bytes);
+/* the same for a blob that already sits in this GPU's memory (the receive buffer of the broadcast, 8-byte aligned):
+ * the payload never travels through the host, one scatter launch applies it; the caller keeps the buffer alive until
+ * the connector's stream has passed the call (octree_cuc_sync, or the next frame's completion) */
+void   octree_cuc_apply_blob_device(octree_glc_t* rc, uint64_t blob_device, size_t bytes);
 
 /* device self-test: the fast kernel's hoisted-reciprocal division against the IEEE
  * `/` on `count` operand pairs drawn like the traversal's (see octree_trace_fast.cuh);

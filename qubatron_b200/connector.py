@@ -93,6 +93,7 @@ _PROTOS = {
     "octree_cuc_read_frame_staged": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_void_p, C.c_size_t]),
     "octree_cuc_set_tile_feedback": (None, [C.POINTER(octree_glc_t), C.c_int]),
     "octree_cuc_set_persisting_window": (None, [C.POINTER(octree_glc_t), C.c_size_t]),
+    "octree_cuc_set_occupancy": (None, [C.POINTER(octree_glc_t), C.c_int]),
     "octree_cuc_enable_present": (None, [C.POINTER(octree_glc_t), C.c_int]),
     "octree_cuc_read_window": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_void_p, C.c_size_t, C.POINTER(C.c_int),
                                             C.POINTER(C.c_int)]),
@@ -117,6 +118,7 @@ _PROTOS = {
     "octree_cuc_export_pending": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_void_p, C.c_size_t]),
     "octree_cuc_apply_blob": (None, [C.POINTER(octree_glc_t), C.c_void_p, C.c_size_t]),
     "octree_cuc_version": (C.c_char_p, []),
+    "octree_cuc_apply_blob_device": (None, [C.POINTER(octree_glc_t), C.c_uint64, C.c_size_t]),
     "octree_cuc_set_gpus": (None, [C.POINTER(octree_glc_t), C.c_int, C.c_void_p]),
     "octree_cuc_gpu_count": (C.c_int, [C.POINTER(octree_glc_t)]),
     "octree_cuc_last_step_ms": (C.c_float, [C.POINTER(octree_glc_t)]),
@@ -405,6 +407,9 @@ class OctreeGlc:
     def set_tile_feedback(self, on=True):
         self.lib.octree_cuc_set_tile_feedback(self._p, int(bool(on)))
 
+    def set_occupancy(self, ctas_per_sm):
+        self.lib.octree_cuc_set_occupancy(self._p, int(ctas_per_sm))
+
     def set_persisting_window(self, persist_bytes):
         self.lib.octree_cuc_set_persisting_window(self._p, int(persist_bytes))
 
@@ -512,6 +517,14 @@ class OctreeGlc:
     def apply_blob(self, blob):
         blob = np.ascontiguousarray(blob, dtype=np.uint8)
         self.lib.octree_cuc_apply_blob(self._p, blob.ctypes.data_as(C.c_void_p), blob.nbytes)
+
+    def export_pending_into(self, buf_ptr, capacity):
+        """export_pending into caller memory (e.g. a page-locked tensor); returns the bytes needed / written"""
+        return int(self.lib.octree_cuc_export_pending(self._p, C.c_void_p(int(buf_ptr)) if buf_ptr else None,
+                                                      int(capacity)))
+
+    def apply_blob_device(self, device_ptr, nbytes):
+        self.lib.octree_cuc_apply_blob_device(self._p, int(device_ptr), int(nbytes))
 
     def destroy(self):
         if self.rc.impl:

@@ -339,6 +339,7 @@ struct Impl
     int         fence_rank = 0, fence_n = 1;
     unsigned    fence_seq  = 0;
     cudaEvent_t ev_done    = nullptr; // rank 0: every rank's tiles of the last frame are in the framebuffer
+    int                   cta_cap          = 0; // octree_cuc_set_occupancy: resident CTAs per SM of the fast kernel (0 = all)
     size_t                l2_window_bytes  = 0; // octree_cuc_set_persisting_window
     cudaStream_t          l2_window_stream = nullptr;
     const void*           l2_window_base   = nullptr;
@@ -783,7 +784,26 @@ void launch_generic(Impl* I, const FrameParams& P, unsigned blocks)
 template <int DIV, bool DYN>
 void launch_fast_dyn(Impl* I, const FrameParams& P, unsigned blocks)
 {
-    const size_t smem = (size_t) 3 * P.maxlevel * BLOCK_THREADS * sizeof(int);
+    size_t smem = (size_t) 3 * P.maxlevel * BLOCK_THREADS * sizeof(int);
+    // resident CTAs per SM capped by padding the dynamic shared memory (octree_cuc_set_occupancy): fewer warps per
+    // SM run each of them faster, which is what a latency-bound shard of a frame split over many GPUs wants
+    if (I->cta_cap > 0 && I->cta_cap < QB_MINBLOCKS)
+    {
+        const size_t per_cta = (size_t) (227 * 1024) / (size_t) (I->cta_cap + 1) + 1024; // k fit, k + 1 do not
+        if (per_cta > smem) smem = per_cta;
+        if (smem > 48 * 1024 && !(I->aux_on || I->count_on))
+        {
+            static bool raised[2][2] = {{false, false}, {false, false}};
+            if (!raised[DIV][DYN])
+            {
+                CUDA_OK(cudaFuncSetAttribute(render_fast_kernel<DIV, DYN, false, false>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                raised[DIV][DYN] = true;
+            }
+        }
+        else if (smem > 48 * 1024)
+            smem = 48 * 1024;
+    }
     if (I->aux_on && I->count_on)
         render_fast_kernel<DIV, DYN, true, true><<<blocks, BLOCK_THREADS, smem, I->stream>>>(P);
     else if (I->aux_on)
@@ -1319,6 +1339,7 @@ octree_glc_t octree_glc_init(char* path)
     CUDA_OK(cudaStreamCreateWithFlags(&I->own_stream, cudaStreamNonBlocking));
     I->stream = I->own_stream;
     if (getenv("QB_TILE_FEEDBACK")) I->feedback_on = atoi(getenv("QB_TILE_FEEDBACK")) != 0; // for A/B runs
+    if (getenv("QB_CTA_CAP")) I->cta_cap = atoi(getenv("QB_CTA_CAP"));
     if (getenv("QB_L2_WINDOW_MB")) I->l2_window_bytes = (size_t) atoi(getenv("QB_L2_WINDOW_MB")) << 20, I->l2_window_dirty = true;
     CUDA_OK(cudaEventCreate(&I->ev0));
     CUDA_OK(cudaEventCreate(&I->ev1));
@@ -1545,6 +1566,13 @@ void octree_cuc_set_tile_feedback(octree_glc_t* rc, int on)
 // L2 persisting access-policy window over the head of the static tree's node array (north_star design point 1 as an
 // A/B switch): `persist_bytes` of L2 are set aside (clamped to the device maximum) and the window's lines are marked
 // persisting with the hit ratio that fits them; 0 removes the window.  Applied to the stream the frames run on.
+void octree_cuc_set_occupancy(octree_glc_t* rc, int ctas_per_sm)
+{
+    Impl* I    = impl_of(rc);
+    I->cta_cap = ctas_per_sm;
+    REPLAY(I, octree_cuc_set_occupancy(m, ctas_per_sm));
+}
+
 void octree_cuc_set_persisting_window(octree_glc_t* rc, size_t persist_bytes)
 {
     Impl* I             = impl_of(rc);
@@ -2706,6 +2734,54 @@ void octree_cuc_apply_blob(octree_glc_t* rc, const void* blob_host, size_t bytes
         apply_range(I, payload + (size_t) d.src_word * 4, d.buftype, s, e);
     }
     REPLAY(I, octree_cuc_apply_blob(m, blob_host, bytes));
+    publish_memsize(rc, I);
+}
+
+// The same blob already in DEVICE memory of this connector's GPU (the receive buffer of the broadcast): descriptors
+// are validated from a small host copy, the payload never leaves the device -- one scatter launch applies it.
+void octree_cuc_apply_blob_device(octree_glc_t* rc, uint64_t blob_device, size_t bytes)
+{
+    Impl* I = impl_of(rc);
+    if (!I->replicas.empty()) die("apply_blob_device: a group replicates its uploads itself");
+    if (bytes < 16) return;
+    const char* p = (const char*) (uintptr_t) blob_device;
+    if (((uintptr_t) p & 7) != 0) die("apply_blob_device: the blob must be 8-byte aligned");
+    uint64_t hdr[2];
+    CUDA_OK(cudaMemcpyAsync(hdr, p, 16, cudaMemcpyDeviceToHost, I->stream));
+    CUDA_OK(cudaStreamSynchronize(I->stream));
+    if (hdr[0] > (bytes - 16) / sizeof(RangeDesc) || 16 + hdr[0] * sizeof(RangeDesc) + hdr[1] != bytes || hdr[1] % 4 ||
+        hdr[1] / 4 > 0xffffffffull)
+        die("apply_blob: malformed blob");
+    if (hdr[0] == 0) return;
+    std::vector<RangeDesc> descs(hdr[0]);
+    CUDA_OK(cudaMemcpyAsync(descs.data(), p + 16, hdr[0] * sizeof(RangeDesc), cudaMemcpyDeviceToHost, I->stream));
+    CUDA_OK(cudaStreamSynchronize(I->stream));
+    uint64_t next_src = 0;
+    for (const RangeDesc& d : descs)
+    {
+        if (d.buftype < 0 || d.buftype > 5) die("apply_blob: descriptor with an unknown buffer type");
+        if (d.nwords == 0 || ((uint64_t) d.src_word + d.nwords) * 4 > hdr[1]) die("apply_blob: descriptor outside the payload");
+        if (d.src_word != next_src) die("apply_blob: descriptors must tile the payload in order");
+        next_src = (uint64_t) d.src_word + d.nwords;
+        const uint64_t item = is_octree(d.buftype) ? 16 : 12;
+        if ((d.dst_word * 4) % item || ((uint64_t) d.nwords * 4) % item) die("apply_blob: range is not texel-aligned");
+        if (is_octree(d.buftype) && (d.dst_word + d.nwords + 11) / 12 > (uint64_t) CHILD_INDEX_MASK - 1)
+            die("apply_blob: range beyond the node limit");
+    }
+    if (next_src * 4 != hdr[1]) die("apply_blob: descriptors must tile the payload in order");
+    flush_pending(I); // call order is preserved against ranges this connector received directly
+    for (const RangeDesc& d : descs)
+    {
+        const size_t e = ((size_t) d.dst_word + d.nwords) * 4;
+        ensure_capacity(I, d.buftype, e);
+        note_extent(I, d.buftype, e);
+    }
+    const unsigned words = (unsigned) (hdr[1] / 4);
+    scatter_ranges_kernel<<<(words + 255) / 256, 256, 0, I->stream>>>(
+        (const RangeDesc*) (p + 16), (int) hdr[0], (const int*) (p + 16 + hdr[0] * sizeof(RangeDesc)), words,
+        scatter_targets(I));
+    CUDA_OK(cudaGetLastError());
+    I->launches++;
     publish_memsize(rc, I);
 }
 

@@ -110,6 +110,8 @@ class ShardedFrame:
         self.frame_t = None
         self.out_t = None
         self.fence = torch.zeros(1, device=device)
+        self._blob_dev = self._blob_pin = None
+        self._blob_applied = False
         rc.set_shard(rank, world, tile, tile)
         if world == 1:
             return
@@ -190,14 +192,42 @@ class ShardedFrame:
         return out
 
     def broadcast_updates(self, device):
-        """Rank 0's range uploads since the last call -> every rank (rank 0 has applied its own already)."""
+        """Rank 0's range uploads since the last call -> every rank (rank 0 has applied its own already).  The blob
+        goes page-locked host -> rank 0's GPU -> NCCL broadcast -> applied from the receive buffer on the device
+        (octree_cuc_apply_blob_device): no pageable copy, nothing through the other ranks' hosts."""
         if self.world == 1:
             return 0
-        blob = self.rc.export_pending() if self.rank == 0 else None
-        blob = broadcast_blob(blob, 0, device)
-        if self.rank != 0:
-            self.rc.apply_blob(blob)
-        return len(blob)
+        torch, dist = self.torch, self.dist
+        if device is None or torch.device(device).type != "cuda":      # CPU (gloo) tests: the host path
+            blob = self.rc.export_pending() if self.rank == 0 else None
+            blob = broadcast_blob(blob, 0, device)
+            if self.rank != 0:
+                self.rc.apply_blob(blob)
+            return len(blob)
+        if self._blob_applied:
+            self.rc.sync()
+            self._blob_applied = False
+        need = self.rc.export_pending_into(0, 0) if self.rank == 0 else 0
+        size = torch.tensor([need], dtype=torch.int64, device=device)
+        dist.broadcast(size, 0)
+        need = int(size.item())
+        if self._blob_dev is None or self._blob_dev.numel() < need:
+            cap = need + need // 4 + 4096
+            self._blob_dev = torch.empty(cap, dtype=torch.uint8, device=device)
+            if self.rank == 0:
+                self._blob_pin = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+        buf = self._blob_dev[:need]
+        if self.rank == 0:
+            self.rc.export_pending_into(self._blob_pin.data_ptr(), need)
+            buf.copy_(self._blob_pin[:need], non_blocking=True)
+        dist.broadcast(buf, 0)
+        if self.rank != 0 and need > 16:
+            # the connector may run on a stream of its own: the blob is complete before it reads it, and (the
+            # buffer is reused) applied before the next broadcast can overwrite it -- rc.sync in the next call
+            torch.cuda.current_stream().synchronize()
+            self.rc.apply_blob_device(buf.data_ptr(), need)
+            self._blob_applied = True
+        return need
 
     def close(self):
         if self.world > 1 and self.gather == "p2p":

@@ -212,7 +212,18 @@ def test_two_connectors_one_gpu_fence_blob_and_staged_readback(scene_random):
     rcs[0].upload_points(col, K.STATIC_COLOR, 0, len(col))       # > 256 KB: flushes the queued node ranges on rank 0
     blob = rcs[0].export_pending()
     assert len(blob) > len(col) * 12
-    rcs[1].apply_blob(blob)
+    # applied from DEVICE memory, as the receive buffer of the NCCL broadcast is (octree_cuc_apply_blob_device);
+    # a third connector takes the same blob through the host path and must end up identical
+    blob_dev = torch.from_numpy(blob.copy()).cuda()
+    rcs[1].apply_blob_device(blob_dev.data_ptr(), len(blob))
+    rcs[1].sync()
+    third = K.OctreeGlc(b"", device=0)
+    third.upload_scene(sc)
+    third.apply_blob(blob)
+    for a, b in zip(third.download_points(False), rcs[1].download_points(False)):
+        assert np.array_equal(a, b)
+    assert np.array_equal(third.download_octree(False), rcs[1].download_octree(False))
+    third.destroy()
     assert len(rcs[0].export_pending()) == 16                    # drained
     both()
     final = S.Scene("upd", sc.pnt_s, col, sc.nrm_s, tree.nodes(), sc.pnt_d, sc.col_d, sc.nrm_d, sc.oct_d)
