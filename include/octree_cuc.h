@@ -109,6 +109,12 @@ void octree_glc_upload_texbuffer_data(octree_glc_t* rc, void* data, int type, si
 void octree_cuc_set_gpus(octree_glc_t* rc, int n, const int* devices);
 int  octree_cuc_gpu_count(octree_glc_t* rc);
 
+/* Errors.  The reference prints and carries on (octree_glc.c L243); the connector prints to stderr and abort()s on
+ * any CUDA error or malformed argument -- it never returns partial state.  An engine that wants to log, save or
+ * unwind first installs a handler: it is called with the message before the abort, and may choose not to return
+ * (longjmp / exit).  Process-wide; NULL removes it. */
+void octree_cuc_set_error_handler(void (*handler)(const char* message, void* user), void* user);
+
 /* choose the CUDA device used by the next octree_glc_init (default: current) */
 void octree_cuc_select_device(int device);
 
@@ -398,6 +404,9 @@ double octree_cuc_take_upload_ms(octree_glc_t* rc);
  * descriptor before it touches anything. */
 void   octree_cuc_enable_replication_log(octree_glc_t* rc, int on);
 size_t octree_cuc_export_pending(octree_glc_t* rc, void* blob_host, size_t capacity);
+/* the same blob written straight into DEVICE memory of this GPU (the send buffer of the broadcast; 8-byte aligned):
+ * the log keeps its payload in page-locked memory, so it moves at PCIe rate; 0 / too small -> the size needed */
+size_t octree_cuc_export_pending_device(octree_glc_t* rc, uint64_t blob_device, size_t capacity);
 void   octree_cuc_apply_blob(octree_glc_t* rc, const void* blob_host, size_t bytes);
 /* the same for a blob that already sits in this GPU's memory (the receive buffer of the broadcast, 8-byte aligned):
  * the payload never travels through the host, one scatter launch applies it; the caller keeps the buffer alive until

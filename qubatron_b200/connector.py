@@ -28,6 +28,7 @@ AUX_MODEL_S, AUX_MODEL_D, AUX_NODE_S, AUX_NODE_D, AUX_SH_NODE_S, AUX_SH_NODE_D =
 AUX_STRIDE = 6
 
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FAST = 0, 1, 2
+ERROR_FN = C.CFUNCTYPE(None, C.c_char_p, C.c_void_p)   # octree_cuc_set_error_handler
 DIV_GLSL, DIV_IEEE = 0, 1
 PARTICLES, DUST = 0, 1          # octree_cuc_particles_*: particle_vsh.c / dust_vsh.c
 
@@ -94,6 +95,7 @@ _PROTOS = {
     "octree_cuc_set_tile_feedback": (None, [C.POINTER(octree_glc_t), C.c_int]),
     "octree_cuc_set_persisting_window": (None, [C.POINTER(octree_glc_t), C.c_size_t]),
     "octree_cuc_set_occupancy": (None, [C.POINTER(octree_glc_t), C.c_int]),
+    "octree_cuc_set_error_handler": (None, [C.c_void_p, C.c_void_p]),
     "octree_cuc_enable_present": (None, [C.POINTER(octree_glc_t), C.c_int]),
     "octree_cuc_read_window": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_void_p, C.c_size_t, C.POINTER(C.c_int),
                                             C.POINTER(C.c_int)]),
@@ -118,6 +120,7 @@ _PROTOS = {
     "octree_cuc_export_pending": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_void_p, C.c_size_t]),
     "octree_cuc_apply_blob": (None, [C.POINTER(octree_glc_t), C.c_void_p, C.c_size_t]),
     "octree_cuc_version": (C.c_char_p, []),
+    "octree_cuc_export_pending_device": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_uint64, C.c_size_t]),
     "octree_cuc_apply_blob_device": (None, [C.POINTER(octree_glc_t), C.c_uint64, C.c_size_t]),
     "octree_cuc_set_gpus": (None, [C.POINTER(octree_glc_t), C.c_int, C.c_void_p]),
     "octree_cuc_gpu_count": (C.c_int, [C.POINTER(octree_glc_t)]),
@@ -522,6 +525,9 @@ class OctreeGlc:
         """export_pending into caller memory (e.g. a page-locked tensor); returns the bytes needed / written"""
         return int(self.lib.octree_cuc_export_pending(self._p, C.c_void_p(int(buf_ptr)) if buf_ptr else None,
                                                       int(capacity)))
+
+    def export_pending_device(self, device_ptr, capacity):
+        return int(self.lib.octree_cuc_export_pending_device(self._p, int(device_ptr), int(capacity)))
 
     def apply_blob_device(self, device_ptr, nbytes):
         self.lib.octree_cuc_apply_blob_device(self._p, int(device_ptr), int(nbytes))

@@ -29,23 +29,32 @@ namespace
 
 using namespace qb;
 
+// Errors: the message goes to stderr and to the host's handler (octree_cuc_set_error_handler), then the process
+// aborts -- unless the handler does not return (longjmp, exit).  The connector never returns partial state and never
+// falls back to the CPU.
+typedef void (*error_fn_t)(const char*, void*);
+error_fn_t g_error_fn   = nullptr;
+void*      g_error_user = nullptr;
+
+[[noreturn]] void die(const char* msg)
+{
+    fprintf(stderr, "octree_cuc: %s\n", msg);
+    if (g_error_fn) g_error_fn(msg, g_error_user);
+    abort();
+}
+
 #define CUDA_OK(call)                                                                                                 \
     do                                                                                                                \
     {                                                                                                                 \
         cudaError_t e__ = (call);                                                                                     \
         if (e__ != cudaSuccess)                                                                                       \
         {                                                                                                             \
-            fprintf(stderr, "octree_cuc: CUDA error %s at %s:%d: %s\n", cudaGetErrorName(e__), __FILE__, __LINE__,    \
-                    cudaGetErrorString(e__));                                                                         \
-            abort();                                                                                                  \
+            char m__[512];                                                                                            \
+            snprintf(m__, sizeof(m__), "CUDA error %s at %s:%d: %s", cudaGetErrorName(e__), __FILE__, __LINE__,       \
+                     cudaGetErrorString(e__));                                                                        \
+            die(m__);                                                                                                 \
         }                                                                                                             \
     } while (0)
-
-[[noreturn]] void die(const char* msg)
-{
-    fprintf(stderr, "octree_cuc: %s\n", msg);
-    abort();
-}
 
 // ---------------------------------------------------------------------------
 // relayout kernels: the host side speaks the reference's formats (12-int nodes,
@@ -354,7 +363,37 @@ struct Impl
     // replication log (octree_cuc_enable_replication_log): every range this connector applied since the last export
     bool                   repl_on = false;
     std::vector<RangeDesc> repl_descs;
-    std::vector<char>      repl_payload;
+    // payload of the logged ranges in page-locked memory: it goes to the device at PCIe rate (export_pending_device)
+    struct PinnedLog
+    {
+        char*  ptr = nullptr;
+        size_t used = 0, cap = 0;
+        size_t size() const { return used; }
+        bool   empty() const { return used == 0; }
+        void   clear() { used = 0; }
+        const char* data() const { return ptr; }
+        void append(const char* src, size_t n)
+        {
+            if (used + n > cap)
+            {
+                size_t ncap = (used + n) + (used + n) / 2 + (1u << 20);
+                char*  np   = nullptr;
+                if (cudaMallocHost(&np, ncap) != cudaSuccess) die("replication log: cannot allocate page-locked memory");
+                if (used) memcpy(np, ptr, used);
+                if (ptr) cudaFreeHost(ptr);
+                ptr = np;
+                cap = ncap;
+            }
+            memcpy(ptr + used, src, n);
+            used += n;
+        }
+        void release()
+        {
+            if (ptr) cudaFreeHost(ptr);
+            ptr  = nullptr;
+            used = cap = 0;
+        }
+    } repl_payload;
 };
 
 // run `call` (which names the member connector `m`) on every connector of the group behind a primary
@@ -1372,6 +1411,7 @@ void octree_cuc_destroy(octree_glc_t* rc)
     for (auto& r : I->replicas) octree_cuc_destroy(&r);
     I->replicas.clear();
     CUDA_OK(cudaSetDevice(I->device));
+    I->repl_payload.release();
     if (I->fence_words)
     {
         cudaFree(I->fence_words);
@@ -1477,7 +1517,7 @@ void upload_one(octree_glc_t* rc, void* data, int type, size_t size, size_t item
             d.pad      = 0;
             if (I->repl_payload.size() + (e - s) >= ((size_t) 1 << 34)) die("replication log exceeds 16 GiB: export it");
             I->repl_descs.push_back(d);
-            I->repl_payload.insert(I->repl_payload.end(), (const char*) data + s, (const char*) data + e);
+            I->repl_payload.append((const char*) data + s, e - s);
         }
     }
     publish_memsize(rc, I);
@@ -1566,6 +1606,12 @@ void octree_cuc_set_tile_feedback(octree_glc_t* rc, int on)
 // L2 persisting access-policy window over the head of the static tree's node array (north_star design point 1 as an
 // A/B switch): `persist_bytes` of L2 are set aside (clamped to the device maximum) and the window's lines are marked
 // persisting with the hit ratio that fits them; 0 removes the window.  Applied to the stream the frames run on.
+void octree_cuc_set_error_handler(void (*handler)(const char* message, void* user), void* user)
+{
+    g_error_fn   = handler;
+    g_error_user = user;
+}
+
 void octree_cuc_set_occupancy(octree_glc_t* rc, int ctas_per_sm)
 {
     Impl* I    = impl_of(rc);
@@ -2698,6 +2744,29 @@ size_t octree_cuc_export_pending(octree_glc_t* rc, void* blob_host, size_t capac
     memcpy(p, hdr, 16);
     if (nd) memcpy(p + 16, I->repl_descs.data(), nd * sizeof(RangeDesc));
     if (!I->repl_payload.empty()) memcpy(p + 16 + nd * sizeof(RangeDesc), I->repl_payload.data(), I->repl_payload.size());
+    I->repl_descs.clear();
+    I->repl_payload.clear();
+    return need;
+}
+
+// The same blob written straight into DEVICE memory (the send buffer of the broadcast), payload from the page-locked
+// log at PCIe rate; the connector's stream is synchronised before the log is cleared.
+size_t octree_cuc_export_pending_device(octree_glc_t* rc, uint64_t blob_device, size_t capacity)
+{
+    Impl* I = impl_of(rc);
+    if (!I->repl_on) die("export_pending: call octree_cuc_enable_replication_log first (ranges already applied are gone)");
+    const size_t nd   = I->repl_descs.size();
+    const size_t need = 16 + nd * sizeof(RangeDesc) + I->repl_payload.size();
+    if (blob_device == 0 || capacity < need) return need;
+    uint64_t hdr[2] = {(uint64_t) nd, (uint64_t) I->repl_payload.size()};
+    char*    p      = (char*) (uintptr_t) blob_device;
+    CUDA_OK(cudaMemcpyAsync(p, hdr, 16, cudaMemcpyHostToDevice, I->stream));
+    if (nd)
+        CUDA_OK(cudaMemcpyAsync(p + 16, I->repl_descs.data(), nd * sizeof(RangeDesc), cudaMemcpyHostToDevice, I->stream));
+    if (!I->repl_payload.empty())
+        CUDA_OK(cudaMemcpyAsync(p + 16 + nd * sizeof(RangeDesc), I->repl_payload.data(), I->repl_payload.size(),
+                                cudaMemcpyHostToDevice, I->stream));
+    CUDA_OK(cudaStreamSynchronize(I->stream));
     I->repl_descs.clear();
     I->repl_payload.clear();
     return need;

@@ -110,7 +110,7 @@ class ShardedFrame:
         self.frame_t = None
         self.out_t = None
         self.fence = torch.zeros(1, device=device)
-        self._blob_dev = self._blob_pin = None
+        self._blob_dev = None
         self._blob_applied = False
         rc.set_shard(rank, world, tile, tile)
         if world == 1:
@@ -193,8 +193,9 @@ class ShardedFrame:
 
     def broadcast_updates(self, device):
         """Rank 0's range uploads since the last call -> every rank (rank 0 has applied its own already).  The blob
-        goes page-locked host -> rank 0's GPU -> NCCL broadcast -> applied from the receive buffer on the device
-        (octree_cuc_apply_blob_device): no pageable copy, nothing through the other ranks' hosts."""
+        goes from the connector's page-locked log to rank 0's GPU (octree_cuc_export_pending_device), through one NCCL
+        broadcast, and is applied from the receive buffer on the device (octree_cuc_apply_blob_device): no pageable
+        copy, nothing through the other ranks' hosts."""
         if self.world == 1:
             return 0
         torch, dist = self.torch, self.dist
@@ -207,19 +208,15 @@ class ShardedFrame:
         if self._blob_applied:
             self.rc.sync()
             self._blob_applied = False
-        need = self.rc.export_pending_into(0, 0) if self.rank == 0 else 0
+        need = self.rc.export_pending_device(0, 0) if self.rank == 0 else 0
         size = torch.tensor([need], dtype=torch.int64, device=device)
         dist.broadcast(size, 0)
         need = int(size.item())
         if self._blob_dev is None or self._blob_dev.numel() < need:
-            cap = need + need // 4 + 4096
-            self._blob_dev = torch.empty(cap, dtype=torch.uint8, device=device)
-            if self.rank == 0:
-                self._blob_pin = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+            self._blob_dev = torch.empty(need + need // 4 + 4096, dtype=torch.uint8, device=device)
         buf = self._blob_dev[:need]
         if self.rank == 0:
-            self.rc.export_pending_into(self._blob_pin.data_ptr(), need)
-            buf.copy_(self._blob_pin[:need], non_blocking=True)
+            self.rc.export_pending_device(buf.data_ptr(), need)   # page-locked log -> send buffer, stream-ordered
         dist.broadcast(buf, 0)
         if self.rank != 0 and need > 16:
             # the connector may run on a stream of its own: the blob is complete before it reads it, and (the

@@ -59,3 +59,27 @@ def test_product_does_not_touch_the_oracle():
                 for needle in ("qb_oracle", "import oracle", "from oracle", "liboctree_fsh_oracle", "libqubatron_ref",
                                "_ref/"):
                     assert needle not in txt, (dirpath, f, needle)
+
+
+def test_error_handler_is_called_before_the_abort():
+    """octree_cuc_set_error_handler: the engine's hook sees the message, then the process aborts (never partial
+    state).  Triggered without a GPU: a connector used before octree_glc_init."""
+    import os
+    import sys
+    code = r'''
+import ctypes as C, sys
+from qubatron_b200 import connector as K
+lib = K.load_library()
+@K.ERROR_FN
+def handler(msg, user):
+    sys.stdout.write("HANDLER: " + msg.decode() + "\n"); sys.stdout.flush()
+lib.octree_cuc_set_error_handler(C.cast(handler, C.c_void_p), None)
+rc = K.octree_glc_t()
+lib.octree_cuc_sync(C.byref(rc))
+print("RETURNED")
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                       timeout=120)
+    assert r.returncode != 0 and "RETURNED" not in r.stdout
+    assert "HANDLER: connector used before octree_glc_init" in r.stdout, r.stdout[-400:]
