@@ -1167,7 +1167,7 @@ void render_views(octree_glc_t* rc, int n, float width, float height, const floa
                 // after the frame: this view's next order from the costs just measured (not part of ev0..ev1)
                 CUDA_OK(cudaEventRecord(I->ev1, I->stream));
                 ev1_recorded = true;
-                tile_rank_kernel<<<(P.tiles_mine + 127) / 128, 128, 0, I->stream>>>(
+                tile_rank_kernel<<<(P.tiles_mine * 32 + 255) / 256, 256, 0, I->stream>>>(
                     I->cost_dev[I->cost_phase], P.tiles_mine, I->order_dev + (size_t) order_slot * I->order_cap,
                     I->cost_dev[I->cost_phase ^ 1]);
                 I->cost_phase ^= 1;

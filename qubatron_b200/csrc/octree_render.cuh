@@ -146,21 +146,29 @@ __global__ void fence_wait_done_kernel(const unsigned* local, int n, unsigned se
     if (threadIdx.x > 0 && threadIdx.x < (unsigned) n) fence_spin(local + threadIdx.x, seq);
 }
 
-// order[r] = the tile with the r-th largest cost (ties in tile order); clears the cost array of the next frame
+// order[r] = the tile with the r-th largest cost (ties in tile order); clears the cost array of the next frame.
+// One warp per tile, its lanes stride over the other tiles (n = 510 at 1080p: 16 independent loads per lane; the
+// one-thread-per-tile loop this replaces took 11 us of every step, 1.6 % of a 1080p frame).
 __global__ void tile_rank_kernel(const unsigned* __restrict__ cost, int n, int* __restrict__ order,
                                  unsigned* __restrict__ next_cost)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const unsigned c = cost[i];
+    const int i    = (int) ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = (int) (threadIdx.x & 31u);
+    if (i >= n) return; // whole warps: blockDim is a multiple of 32
+    const unsigned c = __ldg(cost + i);
     int            r = 0;
-    for (int j = 0; j < n; j++)
+    for (int j = lane; j < n; j += 32)
     {
         const unsigned cj = __ldg(cost + j);
         r += (cj > c || (cj == c && j < i)) ? 1 : 0;
     }
-    order[r]     = i;
-    next_cost[i] = 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    if (lane == 0)
+    {
+        order[r]     = i;
+        next_cost[i] = 0;
+    }
 }
 __global__ void tile_identity_kernel(int* __restrict__ order, int n)
 {

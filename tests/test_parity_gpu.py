@@ -825,6 +825,38 @@ def test_presentation_at_full_size_equals_the_oracle(scene_c1):
     rc.destroy()
 
 
+def test_tuning_switches_do_not_change_the_frame(scene_random):
+    """octree_cuc_set_occupancy (resident CTAs per SM capped by shared-memory padding, incl. the > 48 KB opt-in) and
+    octree_cuc_set_persisting_window (L2 access-policy window): frames, flags and hit indices stay identical."""
+    rc = K.OctreeGlc(b"", device=0)
+    rc.upload_scene(scene_random)
+    rc.enable_aux(True)
+    pos, ang = (760.0, 200.0, 420.0), (-0.05, -0.12, 0.0)
+
+    def frame():
+        rc.update(400, 230, pos, ang)
+        f, a = rc.read_aux()
+        return rc.read_frame().copy(), f, a
+
+    want = frame()
+    assert (want[1] & K.FLAG_LEAF).any()
+    for cap in (5, 3, 1, 0):
+        rc.set_occupancy(cap)
+        for g, e in zip(frame(), want):
+            assert np.array_equal(g, e), cap
+    rc.enable_aux(False)
+    want_rgba = want[0]
+    for cap in (2, 1, 0):                       # the plain instantiation takes the large-shared-memory opt-in
+        rc.set_occupancy(cap)
+        rc.update(400, 230, pos, ang)
+        assert np.array_equal(rc.read_frame(), want_rgba), cap
+    for mb in (32, 0):
+        rc.set_persisting_window(mb << 20)
+        rc.update(400, 230, pos, ang)
+        assert np.array_equal(rc.read_frame(), want_rgba), mb
+    rc.destroy()
+
+
 def test_tile_feedback_changes_the_order_not_the_frame(scene_c1):
     """Tile scheduling by measured cost (octree_cuc_set_tile_feedback): whatever order the tiles are launched in --
     image order, the order learned from the previous rendering of the view, an order inherited from another view,
