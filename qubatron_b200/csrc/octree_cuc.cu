@@ -348,6 +348,7 @@ struct Impl
     int         fence_rank = 0, fence_n = 1;
     unsigned    fence_seq  = 0;
     cudaEvent_t ev_done    = nullptr; // rank 0: every rank's tiles of the last frame are in the framebuffer
+    bool                  smem_optin[2][2] = {{false, false}, {false, false}};
     int                   cta_cap          = 0; // octree_cuc_set_occupancy: resident CTAs per SM of the fast kernel (0 = all)
     size_t                l2_window_bytes  = 0; // octree_cuc_set_persisting_window
     cudaStream_t          l2_window_stream = nullptr;
@@ -832,12 +833,11 @@ void launch_fast_dyn(Impl* I, const FrameParams& P, unsigned blocks)
         if (per_cta > smem) smem = per_cta;
         if (smem > 48 * 1024 && !(I->aux_on || I->count_on))
         {
-            static bool raised[2][2] = {{false, false}, {false, false}};
-            if (!raised[DIV][DYN])
+            if (!I->smem_optin[DIV][DYN]) // per connector = per device: the attribute belongs to the device's context
             {
                 CUDA_OK(cudaFuncSetAttribute(render_fast_kernel<DIV, DYN, false, false>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                raised[DIV][DYN] = true;
+                I->smem_optin[DIV][DYN] = true;
             }
         }
         else if (smem > 48 * 1024)
