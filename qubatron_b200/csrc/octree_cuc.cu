@@ -831,7 +831,7 @@ void launch_fast_dyn(Impl* I, const FrameParams& P, unsigned blocks)
     {
         const size_t per_cta = (size_t) (227 * 1024) / (size_t) (I->cta_cap + 1) + 1024; // k fit, k + 1 do not
         if (per_cta > smem) smem = per_cta;
-        if (smem > 48 * 1024 && !(I->aux_on || I->count_on))
+        if (smem > 47 * 1024 && !(I->aux_on || I->count_on))
         {
             if (!I->smem_optin[DIV][DYN]) // per connector = per device: the attribute belongs to the device's context
             {
@@ -840,8 +840,9 @@ void launch_fast_dyn(Impl* I, const FrameParams& P, unsigned blocks)
                 I->smem_optin[DIV][DYN] = true;
             }
         }
-        else if (smem > 48 * 1024)
-            smem = 48 * 1024;
+        else if (smem > 47 * 1024)
+            smem = 47 * 1024; // parity / counting instantiations stay below the 48 KB that needs no opt-in (static
+                              // shared memory counts too): the cap is honoured down to 4 CTAs per SM there
     }
     if (I->aux_on && I->count_on)
         render_fast_kernel<DIV, DYN, true, true><<<blocks, BLOCK_THREADS, smem, I->stream>>>(P);
