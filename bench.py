@@ -481,7 +481,18 @@ class Rig:
             ev[i][1].record(self.stream)
         torch.cuda.synchronize()
         self.barrier()
-        return self.max_over_ranks([a.elapsed_time(b) for a, b in ev])
+        own = [a.elapsed_time(b) for a, b in ev]
+        # The contract's number: each rank times its K steps, the job's time is the MAX over ranks of those totals.
+        # (The sum of per-step maxima over-counts at N > 1: a rank that finished its share of frame i early queues
+        # frame i + 1 at once, and its pixel stores then wait for rank 0 to get there -- the slow frame's excess shows
+        # up in that rank's next step as well.)  Rank 0's own per-step times are the frames' latencies: its step
+        # starts when the previous frame is complete and ends when every rank's tiles of this one have arrived.
+        self.last_total_ms = float(self.max_over_ranks([float(np.sum(own))])[0])
+        t0 = self.torch.tensor(own if self.rank == 0 else [0.0] * len(own), dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t0)
+        self.last_rank0_ms = t0.cpu().numpy()
+        return self.max_over_ranks(own)
 
     def kernel_ms(self, views, n):
         """the connector's own event pair around the render kernel alone (max over ranks), L2 flushed"""
@@ -570,8 +581,9 @@ def leg_moving_camera(rig, poses):
            "path": "30 frames walking from pose 0, a cut, 30 frames walking from pose 3; every view is new"}
     for on in (1, 0):
         rig.rc.set_tile_feedback(on)
-        ms = rig.timed(path, len(path), warmup=0)
-        out["feedback_%s" % ("on" if on else "off")] = {"ms_per_frame": float(ms.mean()), "mrays_s": rays / float(ms.sum()) / 1e3}
+        rig.timed(path, len(path), warmup=0)
+        out["feedback_%s" % ("on" if on else "off")] = {"ms_per_frame": rig.last_total_ms / len(path),
+                                                        "mrays_s": rays / rig.last_total_ms / 1e3}
     rig.rc.set_tile_feedback(1)
     return out
 
@@ -583,9 +595,24 @@ def leg_c5(rig, sc, n=64):
     rng = np.random.default_rng(777)
     pos = np.stack([rng.uniform(150, 1650, n), rng.uniform(90, 330, n), rng.uniform(150, 1650, n)], axis=1)
     ang = np.stack([rng.uniform(0, 2 * np.pi, n), rng.uniform(-0.6, 0.6, n), np.zeros(n)], axis=1)
-    mine = list(range(rank, n, world))
     rig.unshard()
     rc.enable_counters(True)
+    mine = list(range(rank, n, world))
+    if world > 1:
+        # views cost very different amounts (a camera inside a building against one over open terrain): they are
+        # dealt to the ranks by the work a counting pass found in each (longest first, to the least loaded rank),
+        # like a running engine would deal them by the previous frame's cost
+        cost = [0] * n
+        for v in mine:
+            rc.update_views(1920, 1080, pos[[v]], ang[[v]], 0.0, 10, MAXLEVEL, BASESIZE, 0)
+            cost[v] = int(rc.read_counters()["descents"])
+        cost = rig.sum_over_ranks(cost)
+        load, share = [0] * world, [[] for _ in range(world)]
+        for v in sorted(range(n), key=lambda k: (-cost[k], k)):
+            r = min(range(world), key=lambda k: (load[k], k))
+            load[r] += cost[v]
+            share[r].append(v)
+        mine = sorted(share[rank])
     rc.update_views(1920, 1080, pos[mine], ang[mine], 0.0, 10, MAXLEVEL, BASESIZE, 0)
     c = rc.read_counters()
     rc.enable_counters(False)
@@ -606,7 +633,8 @@ def leg_c5(rig, sc, n=64):
     allc = rig.sum_over_ranks(allc)
     return {"views": n, "views_per_gpu": len(mine), "rays": rays, "batch_ms": t, "ms_per_view": t / n,
             "mrays_s": rays / t / 1e3, "crc32_of_view_crcs": zlib.crc32(np.asarray(allc, np.uint32).tobytes()),
-            "note": "device time of the slowest rank for its share of the 64 views (1080p each), L2 flushed"}
+            "note": "device time of the slowest rank for its share of the 64 views (1080p each), L2 flushed; views "
+                    "dealt to the ranks by counted work (longest first)"}
 
 
 def leg_c4(rig, sc, poses, frames=8):
@@ -799,6 +827,7 @@ def _main():
     launches0 = rc.launch_count()
     wall0 = time.time()
     step_ms = rig.timed(poses, args.steps)
+    total_ms_job, rank0_ms = rig.last_total_ms, rig.last_rank0_ms
     wall = time.time() - wall0
     launches = rc.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
@@ -813,23 +842,24 @@ def _main():
     extras = {}
     if not args.no_extras:
         t_extras = time.time()
-        warm = rig.timed(poses, args.steps, warmup=2, flush=False)
-        extras["warm_l2"] = {"ms_per_step": float(warm.mean()),
-                             "mrays_s": sum(rays_of(per_pose[i % len(poses)]) for i in range(args.steps)) / float(warm.sum()) / 1e3,
+        rig.timed(poses, args.steps, warmup=2, flush=False)
+        extras["warm_l2"] = {"ms_per_step": rig.last_total_ms / args.steps,
+                             "mrays_s": sum(rays_of(per_pose[i % len(poses)]) for i in range(args.steps)) / rig.last_total_ms / 1e3,
                              "note": "the timed loop without the L2 flush: the 4 poses' working set (~100 MB of "
                                      "DRAM traffic) stays L2-resident, as it does for a camera that moves slowly"}
         rc.set_tile_feedback(0)
-        off = rig.timed(poses, args.steps, warmup=2)
+        rig.timed(poses, args.steps, warmup=2)
         rc.set_tile_feedback(1)
-        extras["tile_feedback_off"] = {"ms_per_step": float(off.mean()), "note": "tiles in image order (QB_TILE_FEEDBACK=0)"}
+        extras["tile_feedback_off"] = {"ms_per_step": rig.last_total_ms / args.steps, "note": "tiles in image order (QB_TILE_FEEDBACK=0)"}
         extras["moving_camera"] = leg_moving_camera(rig, poses)
         # north_star design point 1 as an A/B: an L2 persisting access-policy window over the head of the static
         # node array (as much as the device allows), same timed loop, L2 flushed before every step
         rc.set_persisting_window(96 << 20)
-        win = rig.timed(poses, args.steps, warmup=len(poses))
+        rig.timed(poses, args.steps, warmup=len(poses))
+        win_ms = rig.last_total_ms / args.steps
         rc.set_persisting_window(0)
         rig.timed(poses, 0, warmup=2)
-        extras["l2_persisting_window"] = {"ms_per_step": float(win.mean()), "persist_mb_requested": 96,
+        extras["l2_persisting_window"] = {"ms_per_step": win_ms, "persist_mb_requested": 96,
                                           "note": "octree_cuc_set_persisting_window(96 MB): the timed loop with the "
                                                   "window on; compare ms_per_step of the headline (window off) and "
                                                   "extras.warm_l2 (nothing flushed at all)"}
@@ -838,11 +868,12 @@ def _main():
             rig.shard(3840, 2160)
             c4k = rig.count(poses)
             crc4k = rig.crc_frames(poses)
-            ms4k = rig.timed(poses, 12, warmup=len(poses))
+            rig.timed(poses, 12, warmup=len(poses))
+            ms4k_total = rig.last_total_ms
             rays4k = sum(rays_of(c4k[i % len(poses)]) for i in range(12))
             k4 = rig.kernel_ms(poses, 8)
             b4 = sum(alg_bytes(c4k[i % len(poses)], 3840, 2160) for i in range(8))
-            extras["c3_2160p"] = {"ms_per_step": float(ms4k.mean()), "mrays_s": rays4k / float(ms4k.sum()) / 1e3,
+            extras["c3_2160p"] = {"ms_per_step": ms4k_total / 12, "mrays_s": rays4k / ms4k_total / 1e3,
                                   "frame_crc32_by_pose": crc4k, "kernel_ms_mean": float(k4.mean()),
                                   "roofline_frac": b4 / (float(k4.sum()) / 1e3) / 1e9 / (measured_peak()[0] * world),
                                   "note": "BASELINE configs[2]: 3840x2160, 12 steps over the 4 poses, L2 flushed"}
@@ -853,7 +884,7 @@ def _main():
 
     if rank == 0:
         total_rays = sum(rays_of(per_pose[i % len(poses)]) for i in range(args.steps))
-        total_ms = float(step_ms.sum())
+        total_ms = total_ms_job
         value = total_rays / total_ms / 1e3
         peak, peak_src = measured_peak()
         # roofline of the render kernel: algorithmic bytes of the frames timed / their kernel durations, against
@@ -870,10 +901,15 @@ def _main():
             "config": bench_config(meta, args, world),
             "ms_per_frame_by_pose": {str(p): float(np.mean([m for q, m in zip(kposes, kt) if q == p]))
                                      for p in range(len(poses))},
-            "step_ms_by_pose": {str(p): float(np.mean([m for i, m in enumerate(step_ms) if i % len(poses) == p]))
+            "step_ms_by_pose": {str(p): float(np.mean([m for i, m in enumerate(rank0_ms) if i % len(poses) == p]))
                                 for p in range(len(poses))},
+            "timing": "value = rays of the K steps / MAX over ranks of each rank's own K-step total (CUDA events on the "
+                      "launch stream around every step, L2 flush outside the pairs); step_ms_by_pose = rank 0's steps "
+                      "(previous frame complete -> every rank's tiles of this frame arrived); the sum of per-step "
+                      "maxima over ranks, which counts the wait behind a slow frame twice at N > 1, would give %.4f "
+                      "ms/step" % (float(step_ms.sum()) / args.steps),
             "rays_per_frame_by_pose": [rays_of(c) for c in per_pose],
-            "mrays_s_by_pose": {str(p): rays_of(per_pose[p]) / float(np.mean([m for i, m in enumerate(step_ms) if i % len(poses) == p])) / 1e3
+            "mrays_s_by_pose": {str(p): rays_of(per_pose[p]) / float(np.mean([m for i, m in enumerate(rank0_ms) if i % len(poses) == p])) / 1e3
                                 for p in range(len(poses))},
             "frame_crc32": crc_info,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s",

@@ -19,8 +19,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <condition_variable>
 #include <functional>
 #include <map>
+#include <memory>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -233,6 +237,66 @@ constexpr size_t BATCH_MAXDESC = 1u << 16;
 constexpr size_t SMALL_RANGE   = 256u << 10; // ranges up to this size are batched
 constexpr int    VIEW_RING     = 4;
 
+// One persistent host thread per member device of an octree_cuc_set_gpus group, for the per-frame launches: queued
+// from the engine's one thread one device after the other they cost ~14 us each (0.11 ms at eight devices, more than
+// half of an 8-GPU 1080p frame); the workers queue them side by side.  A worker spins for ~1 ms after a frame (the
+// next one of a running engine is there by then) and sleeps on a condition variable otherwise.
+struct FrameWorker
+{
+    std::thread             th;
+    std::mutex              m;
+    std::condition_variable cv;
+    std::function<void()>   job;
+    std::atomic<uint64_t>   posted{0}, done{0};
+    std::atomic<bool>       quit{false};
+
+    FrameWorker() { th = std::thread([this]() { loop(); }); }
+    ~FrameWorker()
+    {
+        {
+            std::lock_guard<std::mutex> lk(m);
+            quit.store(true);
+        }
+        cv.notify_one();
+        if (th.joinable()) th.join();
+    }
+    void loop()
+    {
+        uint64_t seen = 0;
+        for (;;)
+        {
+            int spins = 0;
+            while (posted.load(std::memory_order_acquire) == seen && !quit.load())
+            {
+                if (++spins < 20000)
+                    __builtin_ia32_pause();
+                else
+                {
+                    std::unique_lock<std::mutex> lk(m);
+                    cv.wait(lk, [&]() { return posted.load() != seen || quit.load(); });
+                }
+            }
+            if (quit.load()) return;
+            seen = posted.load(std::memory_order_acquire);
+            job();
+            done.store(seen, std::memory_order_release);
+        }
+    }
+    void post(std::function<void()> j)
+    {
+        job = std::move(j);
+        {
+            std::lock_guard<std::mutex> lk(m);
+            posted.fetch_add(1, std::memory_order_release);
+        }
+        cv.notify_one();
+    }
+    void wait()
+    {
+        while (done.load(std::memory_order_acquire) != posted.load(std::memory_order_acquire)) __builtin_ia32_pause();
+    }
+};
+
 struct Impl
 {
     int          device = 0;
@@ -358,6 +422,7 @@ struct Impl
     std::function<void()> deferred;
     // in-process multi-GPU group (octree_cuc_set_gpus): the connectors of the other devices, driven by the same calls
     std::vector<octree_glc_t> replicas;
+    std::vector<std::unique_ptr<FrameWorker>> workers; // one per replica when every member has a device of its own
     bool                      is_replica = false;
     uint8_t*                  ext_flags  = nullptr; // replicas: the primary's parity planes
     int*                      ext_aux    = nullptr;
@@ -1085,6 +1150,7 @@ void render_views(octree_glc_t* rc, int n, float width, float height, const floa
     // kernel stores every pixel of the tiles it owns, discarded ones as (0,0,0,0)
 
     const unsigned blocks = (unsigned) ((size_t) P.tiles_mine * P.blocks_per_tile_x * P.blocks_per_tile_y * n);
+    std::function<void()> rank_tiles; // the tile-ranking launch of this frame, when it is queued after the completion
     // ranks != 0 of a fence: the frame number goes to rank 0 from a 1-warp kernel right behind the render kernel
     auto publish_done = [&]() {
         if (!fenced || I->fence_rank == 0) return;
@@ -1168,11 +1234,22 @@ void render_views(octree_glc_t* rc, int n, float width, float height, const floa
                 // after the frame: this view's next order from the costs just measured (not part of ev0..ev1)
                 CUDA_OK(cudaEventRecord(I->ev1, I->stream));
                 ev1_recorded = true;
-                tile_rank_kernel<<<(P.tiles_mine * 32 + 255) / 256, 256, 0, I->stream>>>(
-                    I->cost_dev[I->cost_phase], P.tiles_mine, I->order_dev + (size_t) order_slot * I->order_cap,
-                    I->cost_dev[I->cost_phase ^ 1]);
+                const unsigned* cost_now  = I->cost_dev[I->cost_phase];
+                unsigned*       cost_next = I->cost_dev[I->cost_phase ^ 1];
+                int*            order_out = I->order_dev + (size_t) order_slot * I->order_cap;
+                const int       nt        = P.tiles_mine;
                 I->cost_phase ^= 1;
-                I->launches++;
+                rank_tiles = [=]() {
+                    tile_rank_kernel<<<(nt * 32 + 255) / 256, 256, 0, I->stream>>>(cost_now, nt, order_out, cost_next);
+                    I->launches++;
+                };
+                // the collecting rank of a fence ranks its tiles AFTER the wait for the other ranks' tiles (below):
+                // the frame is complete a launch earlier
+                if (!(fenced && I->fence_rank == 0))
+                {
+                    rank_tiles();
+                    rank_tiles = nullptr;
+                }
             }
         }
         else
@@ -1224,6 +1301,7 @@ void render_views(octree_glc_t* rc, int n, float width, float height, const floa
             I->launches++;
             CUDA_OK(cudaEventRecord(I->ev_done, I->stream));
         }
+        if (rank_tiles) rank_tiles();
         // octree_glc.c L308-351; after ev1: not part of the frame time
         if (present)
         {
@@ -1283,11 +1361,31 @@ void group_render(octree_glc_t* rc, int n, float width, float height, const floa
         R->ext_flags  = I->aux_on ? I->flags : nullptr;
         R->ext_aux    = I->aux_on ? I->aux : nullptr;
     }
-    // the primary first: its kernel carries the "previous frame consumed" signal the others' stores wait for
     I->defer_completion = true;
-    render_views(rc, n, width, height, positions, angles, lighta, quality, maxlevel, basesize, shoot);
-    I->defer_completion = false;
-    REPLAY(I, render_views(m, n, width, height, positions, angles, lighta, quality, maxlevel, basesize, shoot));
+    if (!I->workers.empty())
+    {
+        // every member on a device of its own: all launches side by side (the order between devices is free,
+        // the gate in the kernels makes the others' stores wait for the primary's kernel)
+        for (size_t k = 0; k < I->replicas.size(); k++)
+        {
+            octree_glc_t* m = &I->replicas[k];
+            I->workers[k]->post([=]() {
+                render_views(m, n, width, height, positions, angles, lighta, quality, maxlevel, basesize, shoot);
+            });
+        }
+        render_views(rc, n, width, height, positions, angles, lighta, quality, maxlevel, basesize, shoot);
+        for (auto& w : I->workers) w->wait();
+        I->defer_completion = false;
+        CUDA_OK(cudaSetDevice(I->device));
+    }
+    else
+    {
+        // members share a device: the primary first, its kernel carries the "previous frame consumed" signal the
+        // others' stores wait for
+        render_views(rc, n, width, height, positions, angles, lighta, quality, maxlevel, basesize, shoot);
+        I->defer_completion = false;
+        REPLAY(I, render_views(m, n, width, height, positions, angles, lighta, quality, maxlevel, basesize, shoot));
+    }
     if (I->deferred)
     {
         I->deferred();
@@ -1409,6 +1507,7 @@ void octree_cuc_destroy(octree_glc_t* rc)
     if (!rc || !rc->impl) return;
     Impl* I = impl_of(rc);
     CUDA_OK(cudaStreamSynchronize(I->stream));
+    I->workers.clear(); // joins the frame workers
     for (auto& r : I->replicas) octree_cuc_destroy(&r);
     I->replicas.clear();
     CUDA_OK(cudaSetDevice(I->device));
@@ -1990,6 +2089,17 @@ void octree_cuc_set_gpus(octree_glc_t* rc, int n, const int* devices)
         M->shard_world = n;
         fence_wire(M, k, n, words);
     }
+    // frame workers when no two members share a device (shards of one GPU -- the test mode -- launch in order)
+    bool distinct = true;
+    for (int a = 0; a < n && distinct; a++)
+        for (int b = a + 1; b < n; b++)
+        {
+            const int da = a ? ((Impl*) I->replicas[a - 1].impl)->device : I->device;
+            const int db = ((Impl*) I->replicas[b - 1].impl)->device;
+            if (da == db) distinct = false;
+        }
+    if (distinct && !getenv("QB_NO_FRAME_WORKERS"))
+        for (int k = 1; k < n; k++) I->workers.emplace_back(new FrameWorker());
     CUDA_OK(cudaSetDevice(I->device));
 }
 
