@@ -707,7 +707,9 @@ def leg_c4(rig, sc, poses, frames=8):
             rows.append(d + [e[0].elapsed_time(e[4]), 1e3 * wall, 1e3 * t_calls, len(edits), blob_bytes, nodes,
                              rc.last_frame_ms()])
     a = np.array(rows, dtype=np.float64)
-    mx = rig.max_over_ranks(list(np.median(a[:, :7], axis=0)))
+    med = list(np.median(a[:, :7], axis=0))
+    mx = rig.max_over_ranks(med)
+    r0 = rig.sum_over_ranks([int(round(v * 1e6)) if rank == 0 else 0 for v in med])   # rank 0's own medians (ns)
     import zlib
     crc = zlib.crc32(rig.sharded.read_frame().tobytes()) if rank == 0 else None
     rig.barrier()
@@ -717,6 +719,12 @@ def leg_c4(rig, sc, poses, frames=8):
             "range_upload_calls_host_ms": float(mx[6]), "broadcast_and_apply_ms": float(mx[2]),
             "render_ms": float(mx[3]), "render_kernel_ms": float(rig.max_over_ranks([float(np.median(a[:, 10]))])[0]),
             "frame_ms": float(mx[4]), "frame_wall_ms": float(mx[5]), "last_frame_crc32": crc,
+            "rank0_stage_ms": {"skin_and_build": r0[0] / 1e6, "range_upload_calls": r0[1] / 1e6,
+                               "export_and_broadcast": r0[2] / 1e6, "render_until_frame_complete": r0[3] / 1e6,
+                               "frame": r0[4] / 1e6,
+                               "note": "the stages as rank 0 -- the rank the engine's calls reach -- sees them on its "
+                                       "stream; in the max-over-ranks figures above the other ranks' broadcast stage "
+                                       "contains their wait for rank 0's upload calls"},
             "note": "medians over the frames, max over ranks; 1080p, pose 0, L2 flushed before every frame; the "
                     "reference runs the rebuild on the CPU (10 M x 12 sequential inserts) and uploads 208 MB"}
 
