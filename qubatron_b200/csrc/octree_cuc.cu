@@ -202,6 +202,87 @@ __global__ void scatter_ranges_kernel(const RangeDesc* __restrict__ descs, int n
 }
 
 // ---------------------------------------------------------------------------
+// Slot records of the fast traversal (octree_types.cuh, TreeDev::slot): slot[8 n + k] = { device index of child k of
+// node n, child-exists mask OF THAT CHILD }, derived from the child array above (which stays the statement of the
+// tree: the generic tracer, the builders and the download read it).  A descent then fetches everything the next
+// expansion needs from the PARENT's record in one 8-byte load, and the expansion loads nothing.
+// Keeping them current: whenever words of node n change, (A) its eight slot records are recomputed and every child
+// learns where its record lives (`parent`), then (B) n's own mask -- it may have changed -- is written into n's
+// record in ITS parent.  Two launches: B reads the parent links and masks A left complete; the check against the
+// record's index skips links a re-pointed slot left stale.  Children have larger indices than their parents, so a
+// bulk upload in chunks fixes a parent's records when the child's chunk arrives.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned own_mask_of(const int* child_dev0, unsigned dev_node)
+{
+    const int2 w = *(const int2*) (child_dev0 + (size_t) dev_node * 8);
+    return ((unsigned) w.x >> CHILD_MASK_SHIFT) | (((unsigned) w.y >> CHILD_MASK_SHIFT) << 4);
+}
+// (A) for device nodes [first, first + count): all eight records + the children's parent links
+__global__ void derive_slots_kernel(const int* __restrict__ child_dev0, uint2* __restrict__ slot,
+                                    unsigned* __restrict__ parent, size_t first, size_t count)
+{
+    const size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+    if (i >= count * 8) return;
+    const size_t   e   = first * 8 + i; // record index = device node * 8 + octant
+    const unsigned idx = (unsigned) child_dev0[e] & CHILD_INDEX_MASK;
+    slot[e]            = make_uint2(idx, idx ? own_mask_of(child_dev0, idx) : 0u);
+    if (idx) parent[idx] = (unsigned) e;
+}
+// (B) for device nodes [first, first + count): the node's own mask into its record in its parent
+__global__ void propagate_masks_kernel(const int* __restrict__ child_dev0, uint2* __restrict__ slot,
+                                       const unsigned* __restrict__ parent, size_t first, size_t count)
+{
+    const size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const unsigned n  = (unsigned) (first + i);
+    const unsigned pl = parent[n];
+    if (pl != 0u && slot[pl].x == n) slot[pl].y = own_mask_of(child_dev0, n);
+}
+// the same two steps for the nodes touched by a batch of small ranges (one thread per payload word)
+struct SlotTargets
+{
+    const int* child_dev0[2];
+    uint2*     slot[2];
+    unsigned*  parent[2];
+};
+template <int PHASE>
+__global__ void derive_ranges_kernel(const RangeDesc* __restrict__ descs, int ndesc, unsigned int total_words,
+                                     SlotTargets T)
+{
+    unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total_words) return;
+    int lo = 0, hi = ndesc - 1;
+    while (lo < hi)
+    {
+        int mid = (lo + hi + 1) >> 1;
+        if (descs[mid].src_word <= i)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    const RangeDesc d = descs[lo];
+    if (d.buftype != OCTREE_GLC_BUFFER_STATIC_OCTREE && d.buftype != OCTREE_GLC_BUFFER_DYNAMIC_OCTREE) return;
+    const int      t    = d.buftype == OCTREE_GLC_BUFFER_DYNAMIC_OCTREE;
+    const size_t   k    = d.dst_word + (i - d.src_word);
+    const size_t   node = k / 12;
+    const int      s    = (int) (k - node * 12);
+    if (s >= 8) return;
+    const unsigned n = (unsigned) node + 1u; // device node
+    if (PHASE == 0)
+    {
+        const size_t   e   = (size_t) n * 8 + s;
+        const unsigned idx = (unsigned) T.child_dev0[t][e] & CHILD_INDEX_MASK;
+        T.slot[t][e]       = make_uint2(idx, idx ? own_mask_of(T.child_dev0[t], idx) : 0u);
+        if (idx) T.parent[t][idx] = (unsigned) e;
+    }
+    else
+    {
+        const unsigned pl = T.parent[t][n];
+        if (pl != 0u && T.slot[t][pl].x == n) T.slot[t][pl].y = own_mask_of(T.child_dev0[t], n);
+    }
+}
+
+// ---------------------------------------------------------------------------
 // connector state
 // ---------------------------------------------------------------------------
 
@@ -215,6 +296,8 @@ struct Tree
 {
     DevArray child; // 32 B per device node: [0] the all-zero dummy, [n + 1] reference node n, one spare zero slot
     DevArray model; // 4 B per device node
+    DevArray slot;   // 64 B per device node: eight { child index, that child's mask } records (fast traversal)
+    DevArray parent; // 4 B per device node: the record (8 * node + octant) that points to it, 0 = none
     size_t   cap_nodes = 0;        // reference nodes the arrays hold (device nodes: cap_nodes + 2)
     size_t   nodes     = 0;        // highest reference node uploaded + 1
     size_t   sealed    = (size_t) -1; // extent whose clamp slot (device node nodes + 1) has been zeroed
@@ -562,6 +645,40 @@ ScatterTargets scatter_targets(Impl* I)
     return T;
 }
 
+bool is_octree(int buftype);
+
+// slot records of device nodes [first_ref + 1, first_ref + 1 + count) after their words changed (see derive_slots_kernel)
+void derive_slots(Impl* I, int t, size_t first_ref, size_t count)
+{
+    if (count == 0) return;
+    Tree&      T  = I->tree[t];
+    const int* c0 = (const int*) T.child.ptr;
+    derive_slots_kernel<<<(unsigned) ((count * 8 + 255) / 256), 256, 0, I->stream>>>(c0, (uint2*) T.slot.ptr,
+                                                                                     (unsigned*) T.parent.ptr, first_ref + 1, count);
+    propagate_masks_kernel<<<(unsigned) ((count + 255) / 256), 256, 0, I->stream>>>(c0, (uint2*) T.slot.ptr,
+                                                                                   (const unsigned*) T.parent.ptr, first_ref + 1, count);
+    CUDA_OK(cudaGetLastError());
+    I->launches += 2;
+}
+SlotTargets slot_targets(Impl* I)
+{
+    SlotTargets S;
+    for (int t = 0; t < 2; t++)
+    {
+        S.child_dev0[t] = (const int*) I->tree[t].child.ptr;
+        S.slot[t]       = (uint2*) I->tree[t].slot.ptr;
+        S.parent[t]     = (unsigned*) I->tree[t].parent.ptr;
+    }
+    return S;
+}
+void derive_ranges(Impl* I, const RangeDesc* descs_dev, int nd, unsigned words)
+{
+    derive_ranges_kernel<0><<<(words + 255) / 256, 256, 0, I->stream>>>(descs_dev, nd, words, slot_targets(I));
+    derive_ranges_kernel<1><<<(words + 255) / 256, 256, 0, I->stream>>>(descs_dev, nd, words, slot_targets(I));
+    CUDA_OK(cudaGetLastError());
+    I->launches += 2;
+}
+
 void flush_pending(Impl* I)
 {
     if (I->descs.empty()) return;
@@ -574,6 +691,9 @@ void flush_pending(Impl* I)
                                                                        words, scatter_targets(I));
     CUDA_OK(cudaGetLastError());
     I->launches++;
+    bool any_octree = false;
+    for (const RangeDesc& d : I->descs) any_octree = any_octree || is_octree(d.buftype);
+    if (any_octree) derive_ranges(I, I->desc_dev, (int) nd, words);
     // the pinned staging is reused by the next batch
     CUDA_OK(cudaStreamSynchronize(I->stream));
     I->descs.clear();
@@ -608,6 +728,8 @@ bool ensure_capacity(Impl* I, int buftype, size_t size)
         size_t cap = grown(nodes);
         dev_grow(I, T.child, (cap + 2) * 32); // + the dummy in front and the clamp slot behind
         dev_grow(I, T.model, (cap + 2) * 4);
+        dev_grow(I, T.slot, (cap + 2) * 64);
+        dev_grow(I, T.parent, (cap + 2) * 4);
         T.cap_nodes = cap;
         T.sealed    = (size_t) -1;
         return true;
@@ -660,6 +782,7 @@ void upload_bulk(Impl* I, const char* src, int buftype, size_t s, size_t e)
             relayout_octree_kernel<<<blocks, 256, 0, I->stream>>>((const int*) I->stage_dev, off / 4, words,
                                                                   I->tree[t].up_child(), I->tree[t].up_model(),
                                                                   I->tree[t].max_dev());
+        if (is_octree(buftype)) derive_slots(I, t, off / 48, (off + n + 47) / 48 - off / 48);
         else
         {
             int which = (buftype == OCTREE_GLC_BUFFER_STATIC_NORMAL || buftype == OCTREE_GLC_BUFFER_DYNAMIC_NORMAL);
@@ -734,6 +857,7 @@ TreeDev tree_dev(Impl* I, int t)
     }
     TreeDev D;
     D.child = (const int4*) T.child.ptr;
+    D.slot  = (const uint2*) T.slot.ptr;
     D.model = (const int*) T.model.ptr;
     D.nodes = (int) T.nodes + 1;
     return D;
@@ -1522,6 +1646,8 @@ void octree_cuc_destroy(octree_glc_t* rc)
     {
         dev_free(I, I->tree[t].child);
         dev_free(I, I->tree[t].model);
+        dev_free(I, I->tree[t].slot);
+        dev_free(I, I->tree[t].parent);
         dev_free(I, I->pts[t].rec);
     }
     cudaFree(I->stage_dev);
@@ -2265,6 +2391,7 @@ size_t build_from_device_paths(Impl* I, int buftype, const int* p14, const int* 
     launches += 1;
     I->tree[t].nodes = (size_t) total; // like octree_reset + rebuild: the old extent is gone
     I->launches += launches;
+    derive_slots(I, t, 0, (size_t) total);
 
     scratch_free(I, final_of_tmp);
     scratch_free(I, tmp_child);
@@ -2962,6 +3089,7 @@ void octree_cuc_apply_blob_device(octree_glc_t* rc, uint64_t blob_device, size_t
         scatter_targets(I));
     CUDA_OK(cudaGetLastError());
     I->launches++;
+    derive_ranges(I, (const RangeDesc*) (p + 16), (int) hdr[0], words);
     publish_memsize(rc, I);
 }
 

@@ -12,6 +12,11 @@
 //                                   (bit k of the mask = child k > 0), maintained by
 //                                   the upload kernels, so an expansion needs 8 bytes
 //                                   of the node and a descent one more word.
+//   slot_{s,d}  : uint2[8*(nodes+2)] -- derived from child_*: record 8 n + k = { device index of child k of node n,
+//                                   child-exists mask of THAT CHILD }.  A descent of the fast traversal reads one
+//                                   record and has the child's node index and everything the child's expansion
+//                                   needs; the expansion itself loads nothing (the connector keeps the records
+//                                   current through every upload, build and blob: octree_cuc.cu derive_slots)
 //   model_{s,d} : int32[nodes]   -- oct[8] of the node (point index), split out
 //                                   as the reference author wanted
 //                                   (octree_fsh.c L125)
@@ -33,6 +38,7 @@ namespace qb
 // clamped to it with one min, which keeps "reads beyond the uploaded range return 0" without a compare-and-branch.
 struct TreeDev
 {
+    const uint2* slot; // 8 x { child device index, child-exists mask OF THAT CHILD } per device node (fast traversal)
     const int4* child; // 2 x int4 per device node
     const int*  model; // oct[8] per device node
     int         nodes; // reference nodes uploaded so far + 1 = the zero slot every larger index is clamped to
