@@ -518,7 +518,7 @@ class Rig:
         return out
 
 
-def leg_e2e(rig, poses, per_pose, steps):
+def leg_e2e(rig, poses, per_pose, steps, flush=True):
     """The reference-facing call with HOST buffers: pose in (pinned constants, H2D inside octree_glc_update), frame
     out (D2H into page-locked host memory) EVERY step; frame i's copy overlaps the rendering of frame i+1.  Same
     policy at every N: L2 flushed before each step, the flush's own cost measured and subtracted."""
@@ -531,7 +531,8 @@ def leg_e2e(rig, poses, per_pose, steps):
 
     def loop(n):
         for i in range(n):
-            rig.flush()
+            if flush:
+                rig.flush()
             rig.frame(poses[i % len(poses)])
             rig.sharded.read_frame_async(host_frames[i & 1] if rank == 0 else None)
         if rank == 0:
@@ -544,7 +545,7 @@ def leg_e2e(rig, poses, per_pose, steps):
     loop(steps)
     e2e_s = time.time() - t
     tf = 0.0
-    if rig.flush_buf is not None:
+    if flush and rig.flush_buf is not None:
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(rig.stream)
         for _ in range(steps):
@@ -846,6 +847,11 @@ def _main():
     kposes = [i % len(poses) for i in range(nk)]
 
     e2e = leg_e2e(rig, poses, per_pose, args.steps)
+    # the same loop with nothing flushed and nothing subtracted (the scene arrays exceed L2 twenty times over; the
+    # poses' working set stays L2-resident, worth 0.5 % on the kernel -- extras.warm_l2): the plain wall clock
+    nf = leg_e2e(rig, poses, per_pose, args.steps, flush=False)
+    e2e["no_flush"] = {"value": nf["value"], "ms_per_step": nf["ms_per_step"],
+                       "note": "same loop, L2 not flushed between steps, wall clock as it is"}
 
     extras = {}
     if not args.no_extras:
