@@ -44,7 +44,8 @@ def build_cuc(force=False):
     srcs = [os.path.join(csrc, f) for f in os.listdir(csrc)]
     srcs.append(os.path.join(_HERE, "..", "include", "octree_cuc.h"))
     if force or _stale(out, srcs):
-        _run(["make", "-C", csrc] + (["-B"] if force else []))
+        # -B: whatever made the library stale (a header the Makefile does not list, the Makefile itself), rebuild
+        _run(["make", "-B", "-C", csrc] + (["OUT=" + out] if os.environ.get("QB_CUC_LIB") else []))
     return out
 
 
