@@ -43,9 +43,11 @@ def build_cuc(force=False):
     csrc = os.path.join(_HERE, "csrc")
     srcs = [os.path.join(csrc, f) for f in os.listdir(csrc)]
     srcs.append(os.path.join(_HERE, "..", "include", "octree_cuc.h"))
+    if os.environ.get("QB_CUC_LIB"):
+        return out  # a developer's A/B build (scripts/build_variants.sh): used as it is, never rebuilt here
     if force or _stale(out, srcs):
         # -B: whatever made the library stale (a header the Makefile does not list, the Makefile itself), rebuild
-        _run(["make", "-B", "-C", csrc] + (["OUT=" + out] if os.environ.get("QB_CUC_LIB") else []))
+        _run(["make", "-B", "-C", csrc])
     return out
 
 
