@@ -825,6 +825,53 @@ def test_presentation_at_full_size_equals_the_oracle(scene_c1):
     rc.destroy()
 
 
+def test_slot_records_follow_tree_replacement_removals_and_appends():
+    """The fast traversal reads slot records derived from the child array (octree_types.cuh, TreeDev::slot).  They
+    must stay current through everything the reference API can do to a tree: a big tree replaced by a smaller,
+    different one in the same buffers (stale nodes and stale parent links behind the new extent), leaves removed
+    (a parent's slot zeroed, the child's own node never uploaded again), points appended one by one with only the
+    touched 48-byte nodes uploaded (new nodes land on the old tree's stale nodes) -- every frame against the oracle,
+    both kernels (the generic one reads the child array itself)."""
+    big = S.make_random(40000, 6000, seed=21)
+    small = S.make_random(9000, 1500, seed=22)
+    pos, ang = (760.0, 200.0, 420.0), (-0.05, -0.12, 0.0)
+    rc = K.OctreeGlc(b"", device=0)
+    rc.upload_scene(big)
+    _render_and_compare(big, 192, 108, pos, ang, rc=rc, divs=DIVS[:1])
+    # a smaller, different level and figure over the old ones (whole-array uploads, like a level change)
+    rc.upload_scene(small)
+    _render_and_compare(small, 192, 108, pos, ang, rc=rc, divs=DIVS[:1])
+    # zero-and-append on both trees, per-node uploads only
+    rng = np.random.default_rng(23)
+    trees, pts, cols, nrms = [], [], [], []
+    for dyn, (p0, c0, n0) in enumerate(((small.pnt_s, small.col_s, small.nrm_s), (small.pnt_d, small.col_d, small.nrm_d))):
+        t = S.HostOctree()
+        t.insert_points(p0)
+        victims = rng.permutation(len(p0))[:400]
+        touched = []
+        for v in victims:
+            m, o = t.remove_point(p0[v])
+            if o >= 0:
+                touched.append(o)
+        extra = np.clip((p0[rng.integers(0, len(p0), 700)] + rng.normal(0, 4.0, (700, 3))).astype(np.float32), 1.0, 1798.0)
+        for k, q in enumerate(extra):
+            touched.extend(int(j) for j in t.insert_point(q, len(p0) + k) if j > 0)
+        p1 = np.concatenate([p0, extra])
+        c1 = np.concatenate([c0, np.tile(np.array([[0.9, 0.4, 0.1]], np.float32), (len(extra), 1))])
+        n1 = np.concatenate([n0, np.tile(np.array([[0.0, 1.0, 0.0]], np.float32), (len(extra), 1))])
+        bt = K.DYNAMIC_OCTREE if dyn else K.STATIC_OCTREE
+        t.upload_node_ranges(rc, sorted(set(touched)), bt)
+        rc.upload_points(c1, K.DYNAMIC_COLOR if dyn else K.STATIC_COLOR, len(p0), len(p1))
+        rc.upload_points(n1, K.DYNAMIC_NORMAL if dyn else K.STATIC_NORMAL, len(p0), len(p1))
+        trees.append(t.nodes()), pts.append(p1), cols.append(c1), nrms.append(n1)
+        # (the device extent is still the bigger tree's: its nodes behind the new tree are stale, like stale texels)
+        assert np.array_equal(rc.download_octree(dynamic=bool(dyn))[:len(trees[-1])], trees[-1])
+    final = S.Scene("edited", pts[0], cols[0], nrms[0], trees[0], pts[1], cols[1], nrms[1], trees[1])
+    ref, _ = _render_and_compare(final, 192, 108, pos, ang, rc=rc, divs=DIVS[:1])
+    assert ((ref["flags"] & O.FLAG_LEAF) > 0).sum() > 2000 and (ref["aux"][..., K.AUX_MODEL_D] > 0).sum() > 50
+    rc.destroy()
+
+
 def test_tuning_switches_do_not_change_the_frame(scene_random):
     """octree_cuc_set_occupancy (resident CTAs per SM capped by shared-memory padding, incl. the > 48 KB opt-in) and
     octree_cuc_set_persisting_window (L2 access-policy window): frames, flags and hit indices stay identical."""
