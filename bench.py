@@ -9,7 +9,7 @@ Workload (BASELINE.json configs[1]): synthetic ~90 M-point "abandoned-scale" sta
 A step = octree_glc_update() of one frame.  N > 1 (torchrun, one rank per GPU): the octree
 is replicated, the image is split into interleaved 64x64 tiles, every rank renders its
 tiles straight into rank 0's framebuffer over NVLink (peer stores from the render kernel)
-and one small NCCL all-reduce fences the frame.
+and device-side flags complete the frame (octree_cuc_set_fence: no collective per frame).
 
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
 """
