@@ -1033,14 +1033,22 @@ void launch_fast_dyn(Impl* I, const FrameParams& P, unsigned blocks)
             smem = 47 * 1024; // parity / counting instantiations stay below the 48 KB that needs no opt-in (static
                               // shared memory counts too): the cap is honoured down to 4 CTAs per SM there
     }
+#ifdef QB_GRID_LINEAR
+    const unsigned grid = blocks;
+#else
+    // (blocks of a tile, this shard's tiles, views): the kernel reads its place from blockIdx instead of dividing
+    if (P.tiles_mine > 65535 || P.n_views > 65535) die("update: more than 65535 tiles per shard or views in one launch");
+    const dim3 grid((unsigned) (P.blocks_per_tile_x * P.blocks_per_tile_y), (unsigned) P.tiles_mine, (unsigned) P.n_views);
+    if ((size_t) grid.x * grid.y * grid.z != blocks) die("update: launch grid does not cover the frame");
+#endif
     if (I->aux_on && I->count_on)
-        render_fast_kernel<DIV, DYN, true, true><<<blocks, BLOCK_THREADS, smem, I->stream>>>(P);
+        render_fast_kernel<DIV, DYN, true, true><<<grid, BLOCK_THREADS, smem, I->stream>>>(P);
     else if (I->aux_on)
-        render_fast_kernel<DIV, DYN, true, false><<<blocks, BLOCK_THREADS, smem, I->stream>>>(P);
+        render_fast_kernel<DIV, DYN, true, false><<<grid, BLOCK_THREADS, smem, I->stream>>>(P);
     else if (I->count_on)
-        render_fast_kernel<DIV, DYN, false, true><<<blocks, BLOCK_THREADS, smem, I->stream>>>(P);
+        render_fast_kernel<DIV, DYN, false, true><<<grid, BLOCK_THREADS, smem, I->stream>>>(P);
     else
-        render_fast_kernel<DIV, DYN, false, false><<<blocks, BLOCK_THREADS, smem, I->stream>>>(P);
+        render_fast_kernel<DIV, DYN, false, false><<<grid, BLOCK_THREADS, smem, I->stream>>>(P);
 }
 
 void launch_fast(Impl* I, const FrameParams& P, unsigned blocks)
