@@ -83,16 +83,8 @@ __global__ void trace_lines_kernel(const FrameParams P, size_t n, const float* _
 // ---------------------------------------------------------------------------
 // multi-GPU completion fence (FenceDev, octree_types.cuh): device-side flags instead of a collective per frame
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v)
-{
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p)
-{
-    unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
+using ptx::ld_acquire_sys;
+using ptx::st_release_sys;
 constexpr long long FENCE_TIMEOUT_CYCLES = 8000000000ll; // ~4 s: a peer that never answers traps instead of hanging
 __device__ __noinline__ void fence_spin(const unsigned* p, unsigned want)
 {

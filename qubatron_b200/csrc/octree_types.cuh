@@ -26,6 +26,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include "octree_ptx.cuh"
 
 namespace qb
 {

@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(FAST ? BLOCK_THREADS : 256)
     particle_step_kernel(const FrameParams P, size_t n, const float* __restrict__ pos, const float* __restrict__ spd,
                          float* __restrict__ pos_out, float* __restrict__ spd_out, unsigned* __restrict__ finished)
 {
-    extern __shared__ int s_stack[];
+    QB_DYN_SHARED(int, s_stack);
     __shared__ unsigned   s_compact_sel[16];
     FastSmem              fsm{0u, 0u};
     if (FAST) fsm = fast_single_smem(s_stack, s_compact_sel);
