@@ -13,6 +13,7 @@
 #include "skeleton_skin.cuh"
 #include "particle_sim.cuh"
 #include "present.cuh"
+#include "octree_view_host.h"
 
 #include <chrono>
 #include <cmath>
@@ -863,69 +864,6 @@ TreeDev tree_dev(Impl* I, int t)
     return D;
 }
 
-// smallest float d with acosf(d) < 0.02f: the host-libm form of the light-disc
-// test `camangle < 0.02` (octree_fsh.c L418, L452).  acosf is monotone over the
-// scanned interval (checked by tests/test_oracle.py::test_disc_threshold).
-float disc_dot_min()
-{
-    static float cached = 0.0f;
-    if (cached != 0.0f) return cached;
-    uint32_t lo, hi;
-    float    flo = 0.99f, fhi = 1.0f;
-    memcpy(&lo, &flo, 4);
-    memcpy(&hi, &fhi, 4);
-    while (lo < hi) // acosf(lo) >= 0.02 (false), acosf(hi) = 0 < 0.02 (true)
-    {
-        uint32_t mid = lo + (hi - lo) / 2;
-        float    fm;
-        memcpy(&fm, &mid, 4);
-        if (acosf(fm) < 0.02f)
-            hi = mid;
-        else
-            lo = mid + 1;
-    }
-    memcpy(&cached, &hi, 4);
-    return cached;
-}
-
-void host_cross(const float* a, const float* b, float* r)
-{
-    volatile float x = a[1] * b[2] - b[1] * a[2];
-    volatile float y = a[2] * b[0] - b[2] * a[0];
-    volatile float z = a[0] * b[1] - b[0] * a[1];
-    r[0] = x, r[1] = y, r[2] = z;
-}
-// octree_fsh.c L392-395 evaluated on the host in fp32 (per-frame constants)
-void host_quat_rotate(const float* q, const float* v, float* out)
-{
-    float c1[3], t[3], c2[3];
-    host_cross(q, v, c1);
-    for (int i = 0; i < 3; i++)
-    {
-        volatile float m = q[3] * v[i];
-        volatile float s = c1[i] + m;
-        t[i]             = s;
-    }
-    host_cross(q, t, c2);
-    for (int i = 0; i < 3; i++)
-    {
-        volatile float m = 2.0f * c2[i];
-        volatile float s = v[i] + m;
-        out[i]           = s;
-    }
-}
-void host_quat_axis_angle(const float* axis, float angle, float* q)
-{
-    volatile float half = angle * 0.5f;
-    float          sn = sinf(half), cs = cosf(half);
-    for (int i = 0; i < 3; i++)
-    {
-        volatile float m = axis[i] * sn;
-        q[i]             = m;
-    }
-    q[3] = cs;
-}
-
 // bits(m) + maxlevel <= 24 for basesize = m * 2^e, m odd: every cube corner and
 // centre k * basesize / 2^maxlevel is then exact in fp32, level sizes included
 bool grid_is_exact(float basesize, int maxlevel)
@@ -943,50 +881,8 @@ bool grid_is_exact(float basesize, int maxlevel)
 
 void fill_view(Impl* I, ViewParams& V, float ow, const float* position, const float* angle, float lighta, int shoot)
 {
-    const float lightc[3] = {420.0f, 200.0f, 680.0f}; // octree_glc.c L91
-    V.camfp[0]            = position[0];
-    V.camfp[1]            = position[1];
-    V.camfp[2]            = position[2];
-    if (I->light_override)
-    {
-        V.light[0] = I->light[0];
-        V.light[1] = I->light[1];
-        V.light[2] = I->light[2];
-    }
-    else
-    {
-        // octree_glc.c L264: double arithmetic, rounded once on store
-        V.light[0] = lightc[0];
-        V.light[1] = (float) ((double) lightc[1] - (double) sinf(lighta) * 20.0);
-        V.light[2] = (float) ((double) lightc[2] - (double) sinf(lighta) * 200.0);
-    }
     (void) ow;
-    const float yaxis[3] = {0.0f, 1.0f, 0.0f};
-    const float negx[3]  = {-1.0f, 0.0f, 0.0f};
-    float       vx[3];
-    host_quat_axis_angle(yaxis, -angle[0], V.qz); // octree_fsh.c L406-408
-    host_quat_rotate(V.qz, negx, vx);
-    host_quat_axis_angle(vx, -angle[1], V.qx);
-
-    float cl[3];
-    for (int i = 0; i < 3; i++)
-    {
-        volatile float d = V.light[i] - V.camfp[i];
-        cl[i]            = d;
-    }
-    volatile float xx = cl[0] * cl[0], yy = cl[1] * cl[1], zz = cl[2] * cl[2];
-    volatile float s1 = xx + yy;
-    volatile float s2 = s1 + zz;
-    float          l  = sqrtf(s2);
-    volatile float inv = 1.0f / l;
-    for (int i = 0; i < 3; i++)
-    {
-        // normalize(): v * (1/len) under the GLSL lowering, v / len with IEEE division
-        volatile float q = I->div_mode == DIV_GLSL ? cl[i] * inv : cl[i] / l;
-        V.camlight_n[i]  = q;
-    }
-    V.disc_dot_min = disc_dot_min();
-    V.shoot        = shoot;
+    viewhost::fill_view(V, position, angle, lighta, shoot, I->light_override ? I->light : nullptr, I->div_mode == DIV_GLSL);
 }
 
 template <int DIV>
@@ -1062,13 +958,7 @@ void launch_fast(Impl* I, const FrameParams& P, unsigned blocks)
 }
 
 // octree_glc.c L268-269, L288: render size from the window size and the quality setting
-void render_size(float width, float height, uint8_t quality, float& ow, float& oh, int& W, int& H)
-{
-    ow = (float) ((double) width / (6.0 - (double) (float) quality / 2.0));
-    oh = (float) ((double) height / (6.0 - (double) (float) quality / 2.0));
-    W  = (int) ow;
-    H  = (int) oh;
-}
+using viewhost::render_size;
 
 // the connector's own framebuffer / parity planes for `total` pixels (all views of a batch)
 void ensure_frame(Impl* I, size_t total)
@@ -1181,10 +1071,7 @@ void render_views(octree_glc_t* rc, int n, float width, float height, const floa
     {
         ViewParams& V = vh[v];
         fill_view(I, V, ow, positions + 3 * v, angles + 3 * v, lighta, shoot);
-        // octree_fsh.c L403 (tan(PI/4.0) folds to 1.0f)
-        V.cfp[0] = ow / 2.0f;
-        V.cfp[1] = oh / 2.0f;
-        V.cfp[2] = (ow / 2.0f) / 1.0f;
+        viewhost::fill_cfp(V, ow, oh);
     }
     CUDA_OK(cudaMemcpyAsync(vd, vh, n * sizeof(ViewParams), cudaMemcpyHostToDevice, I->stream));
     CUDA_OK(cudaEventRecord(I->slot_ev[slot], I->stream));
