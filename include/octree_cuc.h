@@ -393,6 +393,13 @@ size_t octree_cuc_download_octree(octree_glc_t* rc, octree_glc_buffer_t buftype,
 void octree_cuc_pin_host_buffer(octree_glc_t* rc, void* data, size_t bytes);
 void octree_cuc_unpin_host_buffer(octree_glc_t* rc, void* data);
 
+/* Bulk ranges (> 1 MiB) from PAGEABLE host memory -- what the unmodified engine passes -- are copied into page-locked
+ * staging by `threads` host threads (+ the caller) while the DMA engine moves the previous piece, instead of through
+ * the driver's pageable path (~10 GB/s).  Default 4; 0 = the driver's path.  Single-device connectors only: the
+ * members of an octree_cuc_set_gpus group keep the driver's path.  Page-locked arrays (octree_cuc_pin_host_buffer)
+ * go to the device directly either way. */
+void octree_cuc_set_upload_threads(octree_glc_t* rc, int threads);
+
 /* wall-clock milliseconds the connector spent inside upload calls (host side, including the copies it waited
  * for) since the last call of this function */
 double octree_cuc_take_upload_ms(octree_glc_t* rc);

@@ -114,6 +114,7 @@ _PROTOS = {
     "octree_cuc_download_octree": (C.c_size_t, [C.POINTER(octree_glc_t), C.c_int, C.c_void_p, C.c_size_t]),
     "octree_cuc_pin_host_buffer": (None, [C.POINTER(octree_glc_t), C.c_void_p, C.c_size_t]),
     "octree_cuc_unpin_host_buffer": (None, [C.POINTER(octree_glc_t), C.c_void_p]),
+    "octree_cuc_set_upload_threads": (None, [C.POINTER(octree_glc_t), C.c_int]),
     "octree_cuc_take_upload_ms": (C.c_double, [C.POINTER(octree_glc_t)]),
     "octree_cuc_selftest_div": (C.c_uint64, [C.POINTER(octree_glc_t), C.c_uint64, C.c_uint64]),
     "octree_cuc_debug_order_lut": (None, [C.c_void_p]),
@@ -501,6 +502,10 @@ class OctreeGlc:
 
     def pin_host_buffer(self, arr):
         self.lib.octree_cuc_pin_host_buffer(self._p, arr.ctypes.data_as(C.c_void_p), arr.nbytes)
+
+    def set_upload_threads(self, threads):
+        """host threads that fill the page-locked staging of bulk uploads from pageable memory (0 = driver's path)"""
+        self.lib.octree_cuc_set_upload_threads(self._p, int(threads))
 
     def unpin_host_buffer(self, arr):
         self.lib.octree_cuc_unpin_host_buffer(self._p, arr.ctypes.data_as(C.c_void_p))

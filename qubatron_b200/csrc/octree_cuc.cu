@@ -381,6 +381,124 @@ struct FrameWorker
     }
 };
 
+// Bulk uploads from PAGEABLE host memory (what the unmodified engine passes to octree_glc_upload_texbuffer_data:
+// the [minmodi, maxmodi) colour / normal ranges of a shot, modelutil.c L486-501; the level's arrays at start-up).
+// A plain cudaMemcpy from pageable memory goes through the driver's bounce buffer at ~9-11 GB/s.  Here the range is
+// cut into CHUNK-sized pieces; a few persistent host threads copy piece i + 1 into one of SLOTS page-locked buffers
+// while the DMA engine moves piece i from another at PCIe rate.  Used by single-device connectors; the members of an
+// in-process group keep the driver's path (each device's thread would copy the same source again).
+struct HostStager
+{
+    static constexpr size_t CHUNK = 4u << 20;
+    static constexpr int    SLOTS = 3;
+    char*       pin[SLOTS] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev[SLOTS]  = {nullptr, nullptr, nullptr};
+    bool        used[SLOTS] = {false, false, false};
+    int         next = 0;
+
+    std::vector<std::thread> th;
+    std::mutex               mu;
+    std::condition_variable  cv_go, cv_done;
+    const char*              src = nullptr;
+    char*                    dst = nullptr;
+    size_t                   bytes = 0;
+    unsigned                 gen = 0;
+    int                      pending = 0;
+    bool                     stop = false;
+
+    // slice k of parts: whole cache lines, the tail goes to the last one
+    static void slice(size_t bytes, int parts, int k, size_t& a, size_t& b)
+    {
+        const size_t per = ((bytes / (size_t) parts) + 63) & ~(size_t) 63;
+        a = per * (size_t) k < bytes ? per * (size_t) k : bytes;
+        b = k == parts - 1 ? bytes : (per * (size_t) (k + 1) < bytes ? per * (size_t) (k + 1) : bytes);
+    }
+    void start(int threads)
+    {
+        for (int i = 0; i < SLOTS; i++)
+        {
+            CUDA_OK(cudaMallocHost(&pin[i], CHUNK));
+            CUDA_OK(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+        }
+        const int parts = threads + 1; // the calling thread copies a slice too
+        for (int k = 0; k < threads; k++)
+            th.emplace_back([this, k, parts]() {
+                unsigned seen = 0;
+                for (;;)
+                {
+                    const char* s;
+                    char*       d;
+                    size_t      n;
+                    {
+                        std::unique_lock<std::mutex> lk(mu);
+                        cv_go.wait(lk, [&]() { return stop || gen != seen; });
+                        if (stop) return;
+                        seen = gen, s = src, d = dst, n = bytes;
+                    }
+                    size_t a, b;
+                    slice(n, parts, k + 1, a, b);
+                    if (b > a) memcpy(d + a, s + a, b - a);
+                    {
+                        std::lock_guard<std::mutex> lk(mu);
+                        if (--pending == 0) cv_done.notify_one();
+                    }
+                }
+            });
+    }
+    // memcpy(d, s, n) on all threads
+    void copy(char* d, const char* s, size_t n)
+    {
+        const int parts = (int) th.size() + 1;
+        if (th.empty() || n < (256u << 10))
+        {
+            memcpy(d, s, n);
+            return;
+        }
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            src = s, dst = d, bytes = n, pending = (int) th.size();
+            gen++;
+        }
+        cv_go.notify_all();
+        size_t a, b;
+        slice(n, parts, 0, a, b);
+        if (b > a) memcpy(d + a, s + a, b - a);
+        std::unique_lock<std::mutex> lk(mu);
+        cv_done.wait(lk, [&]() { return pending == 0; });
+    }
+    // dev[0, n) = host[0, n) queued on `st`; returns once the host range has been consumed
+    void h2d(void* dev, const char* host, size_t n, cudaStream_t st)
+    {
+        for (size_t off = 0; off < n; off += CHUNK)
+        {
+            const size_t m = n - off < CHUNK ? n - off : CHUNK;
+            const int    k = next;
+            next           = (next + 1) % SLOTS;
+            if (used[k]) CUDA_OK(cudaEventSynchronize(ev[k])); // the DMA that last read this buffer
+            copy(pin[k], host + off, m);
+            CUDA_OK(cudaMemcpyAsync((char*) dev + off, pin[k], m, cudaMemcpyHostToDevice, st));
+            CUDA_OK(cudaEventRecord(ev[k], st));
+            used[k] = true;
+        }
+    }
+    void shutdown()
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stop = true;
+        }
+        cv_go.notify_all();
+        for (auto& t : th) t.join();
+        th.clear();
+        for (int i = 0; i < SLOTS; i++)
+        {
+            if (ev[i]) cudaEventSynchronize(ev[i]), cudaEventDestroy(ev[i]);
+            if (pin[i]) cudaFreeHost(pin[i]);
+            pin[i] = nullptr, ev[i] = nullptr, used[i] = false;
+        }
+    }
+};
+
 struct Impl
 {
     int          device = 0;
@@ -393,6 +511,10 @@ struct Impl
     Points pts[2];
 
     void* stage_dev = nullptr; // STAGE_BYTES
+    // bulk uploads from pageable memory: page-locked staging filled by `upload_threads` host threads (0 = the driver's
+    // own pageable path); created at the first such upload
+    int                         upload_threads = 4;
+    std::unique_ptr<HostStager> stager;
 
     // pending small ranges
     char*                          batch_host = nullptr; // pinned, BATCH_BYTES
@@ -765,11 +887,28 @@ void upload_bulk(Impl* I, const char* src, int buftype, size_t s, size_t e)
 {
     flush_pending(I);
     const int t = tree_index(buftype);
+    // a large range from pageable memory goes through page-locked staging filled by several host threads (HostStager)
+    bool staged = false;
+    if (I->upload_threads > 0 && e - s >= (1u << 20) && I->replicas.empty() && !I->is_replica)
+    {
+        cudaPointerAttributes at;
+        const cudaError_t     q = cudaPointerGetAttributes(&at, src);
+        if (q != cudaSuccess) (void) cudaGetLastError();
+        staged = q != cudaSuccess || at.type == cudaMemoryTypeUnregistered;
+        if (staged && !I->stager)
+        {
+            I->stager.reset(new HostStager);
+            I->stager->start(I->upload_threads);
+        }
+    }
     for (size_t off = s; off < e; off += STAGE_BYTES)
     {
         size_t n = e - off < STAGE_BYTES ? e - off : STAGE_BYTES;
         // pageable source: the call returns once the range has been consumed
-        CUDA_OK(cudaMemcpyAsync(I->stage_dev, src + (off - s), n, cudaMemcpyHostToDevice, I->stream));
+        if (staged)
+            I->stager->h2d(I->stage_dev, src + (off - s), n, I->stream);
+        else
+            CUDA_OK(cudaMemcpyAsync(I->stage_dev, src + (off - s), n, cudaMemcpyHostToDevice, I->stream));
         size_t   words  = n / 4;
         unsigned blocks = (unsigned) ((words + 255) / 256);
         if (is_octree(buftype) && off % 48 == 0 && n % 48 == 0)
@@ -1497,6 +1636,7 @@ octree_glc_t octree_glc_init(char* path)
     I->stream = I->own_stream;
     if (getenv("QB_TILE_FEEDBACK")) I->feedback_on = atoi(getenv("QB_TILE_FEEDBACK")) != 0; // for A/B runs
     if (getenv("QB_CTA_CAP")) I->cta_cap = atoi(getenv("QB_CTA_CAP"));
+    if (getenv("QB_UPLOAD_THREADS")) I->upload_threads = atoi(getenv("QB_UPLOAD_THREADS")); // for A/B runs
     if (getenv("QB_L2_WINDOW_MB")) I->l2_window_bytes = (size_t) atoi(getenv("QB_L2_WINDOW_MB")) << 20, I->l2_window_dirty = true;
     CUDA_OK(cudaEventCreate(&I->ev0));
     CUDA_OK(cudaEventCreate(&I->ev1));
@@ -1545,6 +1685,8 @@ void octree_cuc_destroy(octree_glc_t* rc)
         dev_free(I, I->tree[t].parent);
         dev_free(I, I->pts[t].rec);
     }
+    if (I->stager) I->stager->shutdown();
+    I->stager.reset();
     cudaFree(I->stage_dev);
     cudaFree(I->batch_dev);
     cudaFree(I->desc_dev);
@@ -2122,6 +2264,17 @@ void octree_cuc_set_gpus(octree_glc_t* rc, int n, const int* devices)
     if (distinct && !getenv("QB_NO_FRAME_WORKERS"))
         for (int k = 1; k < n; k++) I->workers.emplace_back(new FrameWorker());
     CUDA_OK(cudaSetDevice(I->device));
+}
+
+void octree_cuc_set_upload_threads(octree_glc_t* rc, int threads)
+{
+    Impl* I = impl_of(rc);
+    if (threads < 0 || threads > 64) die("set_upload_threads: 0..64");
+    if (threads == I->upload_threads) return;
+    CUDA_OK(cudaStreamSynchronize(I->stream));
+    if (I->stager) I->stager->shutdown();
+    I->stager.reset();
+    I->upload_threads = threads;
 }
 
 void octree_cuc_pin_host_buffer(octree_glc_t* rc, void* data, size_t bytes)
