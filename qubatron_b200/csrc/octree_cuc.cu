@@ -1048,7 +1048,7 @@ void launch_generic(Impl* I, const FrameParams& P, unsigned blocks)
 template <int DIV, bool DYN>
 void launch_fast_dyn(Impl* I, const FrameParams& P, unsigned blocks)
 {
-    size_t smem = (size_t) 3 * P.maxlevel * BLOCK_THREADS * sizeof(int);
+    size_t smem = (size_t) 3 * (P.maxlevel + FAST_RESULT_ROWS) * BLOCK_THREADS * sizeof(int); // levels + result rows
     // resident CTAs per SM capped by padding the dynamic shared memory (octree_cuc_set_occupancy): fewer warps per
     // SM run each of them faster, which is what a latency-bound shard of a frame split over many GPUs wants
     if (I->cta_cap > 0 && I->cta_cap < QB_MINBLOCKS)

@@ -8,8 +8,8 @@
 // model.c L14-25) and are laid out here exactly as the connector's upload kernels lay them out in HBM
 // (octree_types.cuh: child blocks with mask nibbles, slot records, model array, 32-byte point records).
 #include "cuda_host_shim.h"
-extern "C" int qb_emu_dyn_shared[3 * 16 * 128 + 64];
-int            qb_emu_dyn_shared[3 * 16 * 128 + 64];
+extern "C" int qb_emu_dyn_shared[3 * (16 + 4) * 128 + 64];
+int            qb_emu_dyn_shared[3 * (16 + 4) * 128 + 64];
 
 #include "octree_trace_fast.cuh"
 #include "octree_view_host.h"
