@@ -45,6 +45,7 @@ inline void sts_ordered(unsigned addr, unsigned v) { *emu_shared_ptr(addr + OFF)
 template <unsigned OFF>
 inline unsigned lds_ordered(unsigned addr) { return *emu_shared_ptr(addr + OFF); }
 inline unsigned lds_table(unsigned addr) { return *emu_shared_ptr(addr); }
+inline int bfind(unsigned x) { return 31 - __builtin_clz(x); }
 inline unsigned prmt(unsigned a, unsigned b, unsigned sel) // default mode: nibble k of sel picks byte 0-7 of {b, a}
 {
     const unsigned long long src = (unsigned long long) a | ((unsigned long long) b << 32);

@@ -61,11 +61,11 @@ def test_order_lut_equals_the_reference_ordering_loop():
             if b != INF:
                 pts.append((H[0], _side(xy, 9.0, 11.0), _side(xz, 9.0, 11.0), b, 2))
             if c != INF:
-                pts.append((_side(yx, 11.0, 9.0), H[1], _side(yz, 9.0, 11.0), c, 3))
+                pts.append((_side(yx, 11.0, 9.0), H[1], _side(yz, 9.0, 11.0), c, 4))  # kinds are one-hot: z 1, x 2, y 4
             want = _reference_order(pts)
             e = int(lut[idx])
             lo, hi = e & 0xFFFFFFFF, e >> 32
-            got = [((lo >> (8 * i + 3)) & 3, (lo >> (8 * i)) & 7) for i in range(len(pts))]
+            got = [((lo >> (8 * i + 3)) & 7, (lo >> (8 * i)) & 7) for i in range(len(pts))]
             assert got == want, (idx, a, b, c, got, want)
             for i, (_, o) in enumerate(want):
                 assert (hi >> (8 * i)) & 0xFF == 1 << o
@@ -156,7 +156,7 @@ def test_sign_bit_index_and_keep_mask_reproduce_the_reference_on_random_nodes():
             if vx:
                 pts.append((hx, xy, xz, wx, 2))
             if vy:
-                pts.append((yx, hy, yz, wy, 3))
+                pts.append((yx, hy, yz, wy, 4))  # one-hot kinds: z 1, x 2, y 4
             hitp = [list(p) for p in pts]
             want, pre = [], -1
             for i in range(len(hitp)):
@@ -192,7 +192,7 @@ def test_sign_bit_index_and_keep_mask_reproduce_the_reference_on_random_nodes():
                 keep = (((flags * 0x00204081) & 0xFFFFFFFF) >> 26) >> 2
                 lst, n = _prmt_compact(lo, keep)
                 assert n == bin(flags).count("1")
-                got = [((lst >> (8 * i + 3)) & 3, (lst >> (8 * i)) & 7) for i in range(n)]
+                got = [((lst >> (8 * i + 3)) & 7, (lst >> (8 * i)) & 7) for i in range(n)]
                 assert got == want, (case, nan_sign, got, want)
             done += 1
     assert done > 3000 and general > 100, (done, general)
