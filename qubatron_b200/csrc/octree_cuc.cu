@@ -1294,6 +1294,10 @@ void render_views(octree_glc_t* rc, int n, float width, float height, const floa
     P.blocks_per_tile_x = P.tile_w / BLOCK_W;
     P.blocks_per_tile_y = P.tile_h / BLOCK_H;
     const int tiles     = P.tiles_x * P.tiles_y;
+    if (tiles >= 65536 || P.blocks_per_tile_x * P.blocks_per_tile_y >= 65536) die("update: 65536 tiles or more in a frame");
+    auto magic = [](int d) { return d <= 1 ? 0u : (unsigned) (((1ull << 32) + (unsigned) d - 1) / (unsigned) d); }; // 0: d = 1
+    P.tiles_x_magic = magic(P.tiles_x);
+    P.bptx_magic    = magic(P.blocks_per_tile_x);
     P.tiles_mine        = tiles > P.rank ? (tiles - P.rank + P.world - 1) / P.world : 0;
     P.views             = vd;
     P.n_views           = n;

@@ -130,6 +130,7 @@ struct FrameParams
     int tile_w, tile_h, tiles_x, tiles_y;
     int rank, world;
     int blocks_per_tile_x, blocks_per_tile_y;
+    unsigned tiles_x_magic, bptx_magic; // ceil(2^32 / tiles_x), ceil(2^32 / blocks_per_tile_x): n / d = umulhi(n, magic) for n < 65536; 0 when d = 1
     int tiles_mine; // number of tiles this rank renders per view
 
     // tile scheduling by measured cost (fast kernel, single view): launch position -> tile of this rank, heaviest

@@ -45,6 +45,7 @@ static inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned s)
     s &= 31u;
     return s ? (hi << s) | (lo >> (32u - s)) : hi;
 }
+static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned) (((unsigned long long) a * b) >> 32); }
 static inline int  __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int  __clz(int v) { return v ? __builtin_clz((unsigned) v) : 32; }
 static inline int  __float2int_rn(float f) { return (int) lrintf(f); } // round to nearest even (default mode)

@@ -197,6 +197,9 @@ int qb_emu_render(void* scene, float width, float height, int quality, const flo
     P.rank = 0, P.world = 1;
     P.blocks_per_tile_x = P.tile_w / BLOCK_W, P.blocks_per_tile_y = P.tile_h / BLOCK_H;
     P.tiles_mine = P.tiles_x * P.tiles_y;
+    auto magic = [](int d) { return d <= 1 ? 0u : (unsigned) (((1ull << 32) + (unsigned) d - 1) / (unsigned) d); }; // 0: d = 1
+    P.tiles_x_magic = magic(P.tiles_x);
+    P.bptx_magic    = magic(P.blocks_per_tile_x);
     P.views      = &V;
     P.n_views    = 1;
 
