@@ -35,14 +35,6 @@ QB_EMU_F2OP(f2add, +)
 QB_EMU_F2OP(f2sub, -)
 QB_EMU_F2OP(f2mul, *)
 #undef QB_EMU_F2OP
-inline f2 f2fma(f2 a, f2 b, f2 c)
-{
-    float al, ah, bl, bh, cl, ch;
-    f2unpack(a, al, ah);
-    f2unpack(b, bl, bh);
-    f2unpack(c, cl, ch);
-    return f2pack(fmaf(al, bl, cl), fmaf(ah, bh, ch));
-}
 
 static char emu_shared_anchor;
 inline unsigned shared_addr(const void* p) { return (unsigned) (int) ((const char*) p - &emu_shared_anchor); }
@@ -53,12 +45,6 @@ inline void sts_ordered(unsigned addr, unsigned v) { *emu_shared_ptr(addr + OFF)
 template <unsigned OFF>
 inline unsigned lds_ordered(unsigned addr) { return *emu_shared_ptr(addr + OFF); }
 inline unsigned lds_table(unsigned addr) { return *emu_shared_ptr(addr); }
-template <int OFF>
-inline float4 lds_table_v4(unsigned addr)
-{
-    const float* p = (const float*) emu_shared_ptr(addr + (unsigned) OFF);
-    return make_float4(p[0], p[1], p[2], p[3]);
-}
 inline int bfind(unsigned x) { return 31 - __builtin_clz(x); }
 inline unsigned prmt(unsigned a, unsigned b, unsigned sel) // default mode: nibble k of sel picks byte 0-7 of {b, a}
 {

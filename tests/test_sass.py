@@ -3,8 +3,8 @@
 The fast traversal uses Blackwell's packed fp32 instructions (FADD2 / FMUL2, octree_trace_fast_body.inc).  Results stay
 identical to the scalar statement only as long as no packed product is contracted with a packed sum: ptxas does that
 to mul.rn.f32x2 + add.rn.f32x2 whatever the rounding modifiers say, so the source never hands a packed product to a
-packed sum -- and this test makes sure no FFMA2 beyond the one the source asks for (the corner move of a descent, an
-exact product) and no scalar FFMA outside the reciprocals, square roots and the hoisted IEEE division appears."""
+packed sum -- and this test makes sure no FFMA2 (and no scalar FFMA outside the reciprocals, square roots and the hoisted
+IEEE division) appears."""
 import re
 import shutil
 import subprocess
@@ -41,9 +41,7 @@ def test_hot_kernel_is_compiled_for_sm_100a_with_packed_fp32_and_no_contraction(
     assert len(hot) == 16                      # DIV x DYN x AUX x COUNT
     for name, lines in hot.items():
         text = "\n".join(lines)
-        # a contracted packed product would change the rounding; the ONE packed fma is the deliberate one that moves
-        # the cube corner on a descent (corner + bit * edge, bit = 0.0 or 1.0 from the octant table: exact product)
-        assert text.count("FFMA2") == 1, name
+        assert "FFMA2" not in text, name       # a contracted packed product would change the rounding
         glsl = "render_fast_kernelILi0E" in name
         if glsl:
             assert text.count("FADD2") >= 5 and text.count("FMUL2") >= 5, name
