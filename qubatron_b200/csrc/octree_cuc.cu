@@ -218,6 +218,11 @@ __device__ __forceinline__ unsigned own_mask_of(const int* child_dev0, unsigned 
     const int2 w = *(const int2*) (child_dev0 + (size_t) dev_node * 8);
     return ((unsigned) w.x >> CHILD_MASK_SHIFT) | (((unsigned) w.y >> CHILD_MASK_SHIFT) << 4);
 }
+// ... as a slot record carries it (octree_types.cuh SLOT_MASK_REP: the mask in every byte of the word)
+__device__ __forceinline__ unsigned slot_mask_of(const int* child_dev0, unsigned dev_node)
+{
+    return own_mask_of(child_dev0, dev_node) * SLOT_MASK_REP;
+}
 // (A) for device nodes [first, first + count): all eight records + the children's parent links
 __global__ void derive_slots_kernel(const int* __restrict__ child_dev0, uint2* __restrict__ slot,
                                     unsigned* __restrict__ parent, size_t first, size_t count)
@@ -226,7 +231,7 @@ __global__ void derive_slots_kernel(const int* __restrict__ child_dev0, uint2* _
     if (i >= count * 8) return;
     const size_t   e   = first * 8 + i; // record index = device node * 8 + octant
     const unsigned idx = (unsigned) child_dev0[e] & CHILD_INDEX_MASK;
-    slot[e]            = make_uint2(idx, idx ? own_mask_of(child_dev0, idx) : 0u);
+    slot[e]            = make_uint2(idx, idx ? slot_mask_of(child_dev0, idx) : 0u);
     if (idx) parent[idx] = (unsigned) e;
 }
 // (B) for device nodes [first, first + count): the node's own mask into its record in its parent
@@ -237,7 +242,7 @@ __global__ void propagate_masks_kernel(const int* __restrict__ child_dev0, uint2
     if (i >= count) return;
     const unsigned n  = (unsigned) (first + i);
     const unsigned pl = parent[n];
-    if (pl != 0u && slot[pl].x == n) slot[pl].y = own_mask_of(child_dev0, n);
+    if (pl != 0u && slot[pl].x == n) slot[pl].y = slot_mask_of(child_dev0, n);
 }
 // the same two steps for the nodes touched by a batch of small ranges (one thread per payload word)
 struct SlotTargets
@@ -273,13 +278,13 @@ __global__ void derive_ranges_kernel(const RangeDesc* __restrict__ descs, int nd
     {
         const size_t   e   = (size_t) n * 8 + s;
         const unsigned idx = (unsigned) T.child_dev0[t][e] & CHILD_INDEX_MASK;
-        T.slot[t][e]       = make_uint2(idx, idx ? own_mask_of(T.child_dev0[t], idx) : 0u);
+        T.slot[t][e]       = make_uint2(idx, idx ? slot_mask_of(T.child_dev0[t], idx) : 0u);
         if (idx) T.parent[t][idx] = (unsigned) e;
     }
     else
     {
         const unsigned pl = T.parent[t][n];
-        if (pl != 0u && T.slot[t][pl].x == n) T.slot[t][pl].y = own_mask_of(T.child_dev0[t], n);
+        if (pl != 0u && T.slot[t][pl].x == n) T.slot[t][pl].y = slot_mask_of(T.child_dev0[t], n);
     }
 }
 

@@ -13,7 +13,7 @@
 //                                   the upload kernels, so an expansion needs 8 bytes
 //                                   of the node and a descent one more word.
 //   slot_{s,d}  : uint2[8*(nodes+2)] -- derived from child_*: record 8 n + k = { device index of child k of node n,
-//                                   child-exists mask of THAT CHILD }.  A descent of the fast traversal reads one
+//                                   child-exists mask of THAT CHILD, in every byte of the word (SLOT_MASK_REP) }.  A descent of the fast traversal reads one
 //                                   record and has the child's node index and everything the child's expansion
 //                                   needs; the expansion itself loads nothing (the connector keeps the records
 //                                   current through every upload, build and blob: octree_cuc.cu derive_slots)
@@ -51,6 +51,19 @@ __device__ __forceinline__ int tree_clamp(const TreeDev& t, int node)
 // device index -> reference index for reporting (0 for "absent", like the reference's stack)
 __device__ __forceinline__ int ref_node(int dev) { return dev > 0 ? dev - 1 : 0; }
 constexpr int ROOT_NODE = 1;
+
+// The mask half of a slot record (v19): the child's 8-bit child-exists mask REPLICATED into the four bytes of the
+// word, which is the form the expansion tests it in -- the one-hot octants of up to four candidates, one per byte,
+// against the mask in one AND (octree_trace_fast.cuh, g_order_lut value.y).  The replication is paid once, where the
+// record is derived, instead of one multiply per traversal step; the two trees' words are merged by the same
+// three-input logic instruction that applies them, at the END of the expansion -- so the record's load has a whole
+// traversal step to arrive (v18 merged the two masks at the end of the descent: 62 % of the kernel's long-scoreboard
+// stall samples sat on that one instruction, profiles/r2_ncu_v18_*).  -DQB_MASK_PLAIN restores the one-byte mask.
+#ifdef QB_MASK_PLAIN
+constexpr unsigned SLOT_MASK_REP = 1u;
+#else
+constexpr unsigned SLOT_MASK_REP = 0x01010101u;
+#endif
 
 struct PointsDev
 {

@@ -78,7 +78,7 @@ void build_tree(Tree& T, const int* oct, long nodes)
     for (long e = 0; e < 8 * dev_nodes; e++)
     {
         const unsigned idx = (unsigned) c0[e] & CHILD_INDEX_MASK;
-        T.slot[e]          = make_uint2(idx, idx ? own_mask(idx) : 0u);
+        T.slot[e]          = make_uint2(idx, idx ? own_mask(idx) * SLOT_MASK_REP : 0u);
     }
 }
 void build_points(Points& Q, const float* col, const float* nrm, long n)
