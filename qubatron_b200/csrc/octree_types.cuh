@@ -52,17 +52,23 @@ __device__ __forceinline__ int tree_clamp(const TreeDev& t, int node)
 __device__ __forceinline__ int ref_node(int dev) { return dev > 0 ? dev - 1 : 0; }
 constexpr int ROOT_NODE = 1;
 
-// The mask half of a slot record (v19): the child's 8-bit child-exists mask REPLICATED into the four bytes of the
-// word, which is the form the expansion tests it in -- the one-hot octants of up to four candidates, one per byte,
-// against the mask in one AND (octree_trace_fast.cuh, g_order_lut value.y).  The replication is paid once, where the
-// record is derived, instead of one multiply per traversal step; the two trees' words are merged by the same
-// three-input logic instruction that applies them, at the END of the expansion -- so the record's load has a whole
-// traversal step to arrive (v18 merged the two masks at the end of the descent: 62 % of the kernel's long-scoreboard
-// stall samples sat on that one instruction, profiles/r2_ncu_v18_*).  -DQB_MASK_PLAIN restores the one-byte mask.
-#ifdef QB_MASK_PLAIN
-constexpr unsigned SLOT_MASK_REP = 1u;
-#else
+// The mask half of a slot record (v19): the child's 8-bit child-exists mask REPLICATED into the four bytes of the word --
+// the form the expansion tests it in (the one-hot octants of up to four candidates, one per byte, against the mask in
+// one AND: octree_trace_fast.cuh, g_order_lut value.y).  The replication is paid once, where the record is derived,
+// instead of one multiply per traversal step, and the two trees' words are merged by the same three-input logic
+// instruction that applies them, at the END of the expansion: the record loads of a descent have a whole traversal
+// step to arrive (v18 merged the two masks at the end of the descent: 62 % of the kernel's long-scoreboard stall
+// samples sat on that one instruction, profiles/r2_ncu_v18_*).  It pays only together with the unconditional first ray
+// set-up of render_fast_kernel (QB_FIRST_RAY_ALIVE_ONLY there): by itself ptxas parks a wait for the camera-position
+// load, which shares the records' scoreboard, on the first instructions of the expansion
+// (profiles/r2_variants_ab_v19.json, r2_ncu_v19_experiment_scoreboards.txt).  -DQB_MASK_EARLY restores v18's form.
+#if !defined(QB_MASK_EARLY) && !defined(QB_MASK_LATE)
+    #define QB_MASK_LATE 1
+#endif
+#ifdef QB_MASK_LATE
 constexpr unsigned SLOT_MASK_REP = 0x01010101u;
+#else
+constexpr unsigned SLOT_MASK_REP = 1u;
 #endif
 
 struct PointsDev

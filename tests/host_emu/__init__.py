@@ -10,7 +10,9 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "..", "..", "qubatron_b200", "csrc")
-_LIB = os.path.join(_HERE, "libqb_host_emu.so")
+# QB_EMU_DEFINES="-DQB_MASK_LATE ...": the host build of an experiment switch of the kernel source (its own library file)
+_DEFINES = os.environ.get("QB_EMU_DEFINES", "").split()
+_LIB = os.path.join(_HERE, "libqb_host_emu%s.so" % ("_" + "".join(c for c in "".join(_DEFINES) if c.isalnum()) if _DEFINES else ""))
 _lib = None
 
 
@@ -22,7 +24,7 @@ def build(force=False):
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
     cmd = ["g++", "-O2", "-ffp-contract=off", "-fno-fast-math", "-std=c++17", "-w", "-shared", "-fPIC",
            "-DQB_PTX_HOST_HEADER=\"octree_ptx_host.h\"", "-I" + _HERE, "-I" + cuda_inc, "-I" + _CSRC,
-           "-o", _LIB, os.path.join(_HERE, "emu.cpp")]
+           "-o", _LIB, os.path.join(_HERE, "emu.cpp")] + _DEFINES
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("host emulation build failed:\n" + r.stdout)
