@@ -56,3 +56,47 @@ def test_single_ray_kernels_share_the_traversal(sass):
         for n in names:
             text = "\n".join(sass[n])
             assert "FFMA2" not in text and "LDS" in text and "STS" in text, n   # shared-memory stack, no contraction
+
+
+def _control_words(lib, function):
+    """(address, text, scoreboard it sets or None, set of scoreboards it waits for) per instruction: the scheduling
+    control bits of the 128-bit sm_100a encoding as cuobjdump prints it (scripts/sass_scoreboards.py)"""
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    raw = subprocess.run([exe, "-sass", "-fun", function, lib], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                         text=True, check=True).stdout.splitlines()
+    out, i = [], 0
+    while i + 1 < len(raw):
+        m = re.match(r"\s+/\*([0-9a-f]{4})\*/\s+(.*?);\s+/\* 0x([0-9a-f]{16}) \*/", raw[i])
+        m2 = re.match(r"\s+/\* 0x([0-9a-f]{16}) \*/", raw[i + 1]) if m else None
+        if m and m2:
+            hi = int(m2.group(1), 16)
+            wb, wait = (hi >> 46) & 7, (hi >> 52) & 0x3f
+            out.append((int(m.group(1), 16), m.group(2).strip(), None if wb == 7 else wb,
+                        {b for b in range(6) if wait >> b & 1}))
+            i += 2
+        else:
+            i += 1
+    return out
+
+
+def test_nothing_waits_for_the_slot_record_loads_before_the_expansion_applies_them():
+    """Kernel v21's point, as a property of the compiled code: between a descent's two slot-record loads and the
+    order-table load at the end of the expansion, no instruction waits on the scoreboard the record loads set (v18
+    waited at the end of the descent, the v19 experiment six instructions behind the first load: profiles/
+    r2_ncu_v19_experiment_scoreboards.txt).  ptxas decides this, not the source: the test is here so that an edit which
+    brings such a wait back is noticed without a GPU."""
+    try:
+        ins = _control_words(lib_paths()["cuc"], "_ZN2qb18render_fast_kernelILi0ELb1ELb0ELb0EEEvNS_11FrameParamsE")
+    except (OSError, subprocess.CalledProcessError) as e:
+        pytest.skip("cuobjdump unavailable: %r" % (e,))
+    loads = [k for k, (_, text, _, _) in enumerate(ins) if text.startswith("LDG.E.64.CONSTANT")]
+    # in address order: the root's two mask words (set-up), the two slot records of a descent, the order table
+    assert len(loads) == 5, [ins[k][1] for k in loads]
+    s, d, lut = loads[2], loads[3], loads[4]
+    sb = ins[s][2]
+    assert sb is not None and ins[d][2] == sb, (ins[s], ins[d])
+    early = [(hex(a), text) for a, text, _, waits in ins[s + 1:lut] if sb in waits]
+    assert not early, early
+    # ... and the first instruction that does wait for them is the three-input LOP3 that applies both masks
+    first = next((a, text) for a, text, _, waits in ins[lut:] if sb in waits)
+    assert first[1].startswith("LOP3.LUT") and "0xe0" in first[1], first
